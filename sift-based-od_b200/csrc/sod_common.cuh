@@ -1,0 +1,42 @@
+// Shared host-side helpers for the C-ABI translation units: status codes and the thread-local
+// error string behind sod_last_error().
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/sod.h"
+
+namespace sod {
+
+void set_error(const char* fmt, ...);
+int device_sm_count();
+
+#define SOD_CHECK_ARG(cond, ...)        \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::sod::set_error(__VA_ARGS__);    \
+      return SOD_ERR_INVALID_ARGUMENT;  \
+    }                                   \
+  } while (0)
+
+#define SOD_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      ::sod::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                       __LINE__);                                                         \
+      return SOD_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define SOD_CHECK_LAUNCH(name)                                                       \
+  do {                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess) {                                                        \
+      ::sod::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));    \
+      return SOD_ERR_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+
+}  // namespace sod

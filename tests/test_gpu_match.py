@@ -1,0 +1,110 @@
+"""GPU parity: sod_match_top2 / sod_top2_merge vs the oracle (bit-exact indices, distances, flags)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import sift_like
+from oracle import sod_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(q, db, index_base=0):
+    from sod_b200 import engine as E
+    dq = torch.from_numpy(q).cuda()
+    shard = E.prepare_db(torch.from_numpy(db).cuda(), index_base)
+    idx, d2, dist, ok = E.knn_match_ratio(dq, E.Matcher(shard))
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), d2.cpu().numpy(), dist.cpu().numpy(), ok.cpu().numpy().astype(bool)
+
+
+def _check(q, db, index_base=0):
+    idx, d2, dist, ok = _run(q, db, index_base)
+    ridx, rd2 = O.knn2(q, db)
+    ridx = np.where(ridx >= 0, ridx + index_base, -1)
+    bad = np.nonzero((idx != ridx).any(1) | (d2.astype(np.int64) != rd2).any(1))[0]
+    assert bad.size == 0, (f"{bad.size} rows differ, first {bad[:5]}: got {idx[bad[:5]]} {d2[bad[:5]]} "
+                           f"want {ridx[bad[:5]]} {rd2[bad[:5]]}")
+    np.testing.assert_array_equal(dist[ridx[:, 1] >= 0], O.match_distance(rd2)[ridx[:, 1] >= 0])
+    np.testing.assert_array_equal(ok, O.ratio_pass(rd2, ridx))
+
+
+@pytest.mark.parametrize("nq,ndb", [(1, 2), (5, 3), (128, 128), (256, 1000), (257, 129), (300, 4097),
+                                    (1000, 20000), (77, 50001)])
+def test_uniform_u8(nq, ndb):
+    rng = np.random.default_rng(nq * 1000003 + ndb)
+    _check(rng.integers(0, 256, (nq, 128), dtype=np.uint8), rng.integers(0, 256, (ndb, 128), dtype=np.uint8))
+
+
+def test_extreme_values():
+    """All-255 vs all-0 rows reach the largest possible distance 128*255^2."""
+    q = np.zeros((4, 128), np.uint8); q[1] = 255; q[2, ::2] = 255
+    db = np.zeros((300, 128), np.uint8); db[7] = 255; db[9, 1::2] = 255
+    _check(q, db)
+
+
+def test_ties_duplicates_lowest_index_first():
+    """identical database rows -> lowest index first, also for 2nd place and across tiles."""
+    rng = np.random.default_rng(4)
+    db = sift_like(rng, 1000)
+    q = sift_like(rng, 40)
+    for r in (7, 30, 40, 130, 131, 700, 999):
+        db[r] = q[0]
+    db[5] = db[600] = q[1]       # tie across tiles (5 in tile 0, 600 in tile 4)
+    db[128] = db[127] = q[2]     # tie across a tile boundary
+    db[256] = db[0] = q[3]       # column 0 of a later tile vs column 0 of the first
+    idx, d2, _, _ = _run(q, db)
+    assert idx[0].tolist() == [7, 30] and d2[0].tolist() == [0, 0]
+    assert idx[1].tolist() == [5, 600]
+    assert idx[2].tolist() == [127, 128]
+    assert idx[3].tolist() == [0, 256]
+    _check(q, db)
+
+
+def test_sift_like_with_true_matches_and_index_base():
+    rng = np.random.default_rng(100)
+    db = sift_like(rng, 30000)
+    q = sift_like(rng, 3000)
+    hit = rng.choice(3000, 300, replace=False)
+    src = rng.integers(0, 30000, 300)
+    q[hit] = np.clip(db[src].astype(np.int16) + rng.integers(-3, 4, (300, 128)), 0, 255).astype(np.uint8)
+    _check(q, db, index_base=123456)
+    idx, _, _, ok = _run(q, db)
+    assert ok[hit].mean() > 0.9 and (idx[hit, 0] == src).mean() > 0.99
+
+
+def test_ratio_edge_T5():
+    """(d1^2, d2^2) = (18, 32): float32 sqrt makes the reference pass it although 16*18 == 9*32."""
+    from sod_b200 import engine as E
+    pi = torch.tensor([[[0, 1]], [[2, 3]]], dtype=torch.int32).cuda()
+    pd = torch.tensor([[[18, 40]], [[32, 50]]], dtype=torch.int32).cuda()
+    idx, d2, dist, ok = E.merge_top2(pi, pd)
+    assert idx.cpu().tolist() == [[0, 2]] and d2.cpu().tolist() == [[18, 32]]
+    want = O.ratio_pass(np.array([[18, 32]]))
+    assert bool(ok.cpu()[0]) == bool(want[0]) == True
+
+
+def test_merge_matches_oracle_random():
+    from sod_b200 import engine as E
+    rng = np.random.default_rng(9)
+    g, nq = 8, 5000
+    pi = rng.permuted(np.tile(np.arange(g * 2 * 4, dtype=np.int32), (nq, 1)), axis=1)[:, :g * 2]
+    pi = pi.reshape(nq, g, 2).transpose(1, 0, 2).copy()
+    pd = rng.integers(0, 6, (g, nq, 2)).astype(np.int32)      # many equal distances -> index tie-break
+    drop = rng.random((g, nq, 2)) < 0.2
+    pi[drop] = -1; pd[drop] = -1
+    idx, d2, _, ok = E.merge_top2(torch.from_numpy(pi).cuda(), torch.from_numpy(pd).cuda())
+    ri, rd = O.merge_top2(pi, pd.astype(np.int64))
+    np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+    np.testing.assert_array_equal(d2.cpu().numpy().astype(np.int64), rd)
+    np.testing.assert_array_equal(ok.cpu().numpy().astype(bool), O.ratio_pass(rd, ri))
+
+
+def test_pack_from_f32_rejects_non_integer():
+    from sod_b200 import engine as E
+    x = np.random.default_rng(1).integers(0, 256, (100, 128)).astype(np.float32)
+    got = E.pack_descriptors(x).cpu().numpy()
+    np.testing.assert_array_equal(got, x.astype(np.uint8))
+    x[3, 5] = 1.5
+    with pytest.raises(ValueError):
+        E.pack_descriptors(x)
