@@ -29,7 +29,8 @@ extern "C" {
 #define SOD_ERR_UNSUPPORTED (-3)
 
 #define SOD_DESC_DIM 128  /* bytes per descriptor row */
-#define SOD_TILE_ROWS 128 /* database rows per MMA tile; cq arrays are padded to this */
+#define SOD_TILE_ROWS 128 /* database rows per MMA tile */
+#define SOD_CQ_TILE_INTS 132 /* int32 per tile in the prepared `cq` array: 128 keys + 4 chunk minima */
 
 typedef void* sod_stream_t; /* cudaStream_t */
 
@@ -40,8 +41,9 @@ const char* sod_last_error(void);
 /* Number of SMs of the current device (grid sizing; 148 on B200). Negative on error. */
 int sod_device_sm_count(void);
 
-/* rows rounded up to a multiple of SOD_TILE_ROWS: required length of the `cq` array. */
-int64_t sod_padded_rows(int64_t n_rows);
+/* Number of int32 elements of the prepared per-row constants `cq` for a database of n_rows:
+ * ceil(n_rows / SOD_TILE_ROWS) * SOD_CQ_TILE_INTS. */
+int64_t sod_cq_ints(int64_t n_rows);
 
 /* float32 [n_rows,128] -> u8 [n_rows,128].  *nonint_flag (device int32, caller zeroes it) is set
  * to 1 if any value is not an integer in 0..255 (such a set needs the bf16 path, not built yet).
@@ -49,10 +51,11 @@ int64_t sod_padded_rows(int64_t n_rows);
 int sod_pack_u8_from_f32(const float* src, int64_t n_rows, uint8_t* dst, int32_t* nonint_flag,
                          sod_stream_t stream);
 
-/* K1 (database side).  cq[i] = (sum_k db[i][k]^2 << 8) | (i % 128) for i < n_rows and INT32_MAX
- * for the padding rows up to sod_padded_rows(n_rows).  This is the per-row term of
- * |q-t|^2 = |q|^2 + |t|^2 - 2 q.t that OpenCV recomputes per pair inside
- * cv::batchDistance (called from main.py:71). */
+/* K1 (database side).  Per tile of 128 rows, cq holds 128 packed keys
+ * (sum_k db[i][k]^2 << 8) | (i % 128)  (INT32_MAX for rows past the end) followed by the minimum
+ * sum of squares of each 32-row chunk (used to prune the epilogue); sod_cq_ints(n_rows) int32 in
+ * total.  This is the per-row term of |q-t|^2 = |q|^2 + |t|^2 - 2 q.t that OpenCV recomputes per
+ * pair inside cv::batchDistance (called from main.py:71). */
 int sod_db_prepare(const uint8_t* db, int64_t n_rows, int32_t* cq, sod_stream_t stream);
 
 /* K1 (query side).  qn[i] = sum_k q[i][k]^2. */

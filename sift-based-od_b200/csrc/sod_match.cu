@@ -27,6 +27,10 @@
 #include "sod_common.cuh"
 #include "sod_ptx.cuh"
 
+#ifndef SOD_EXP
+#define SOD_EXP 0  // kernel experiments (timing only, results invalid): 1 = no epilogue math, 2 = no TMEM loads
+#endif
+
 namespace sod {
 namespace {
 
@@ -37,6 +41,10 @@ constexpr int kTileN = SOD_TILE_ROWS;       // database rows per MMA
 constexpr int kTileBytes = kTileN * SOD_DESC_DIM;  // 16 KB (A half-tile has the same size)
 constexpr int kStages = 6;
 constexpr int kCqSlots = kStages + 2;       // see the slot-reuse argument in the producer
+constexpr int kChunk = 32;                  // accumulator columns per tcgen05.ld
+constexpr int kCqTile = SOD_CQ_TILE_INTS;   // 128 packed keys + 4 per-chunk minima of |t|^2
+constexpr int kCqTileBytes = kCqTile * 4;   // 528 B, a multiple of 16 for the bulk copy
+constexpr int kInitKey = INT_MAX & ~0xFF;   // "no candidate yet", column byte cleared
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kTmemCols = 512;
@@ -44,14 +52,14 @@ constexpr int kTmemCols = 512;
 constexpr int kOffA = 0;                                    // [2 buffers][2 halves][16 KB]
 constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;     // [kStages][16 KB]
 constexpr int kOffCq = kOffB + kStages * kTileBytes;        // [kCqSlots][128] int32
-constexpr int kOffBar = kOffCq + kCqSlots * kTileN * 4;
+constexpr int kOffBar = kOffCq + kCqSlots * kCqTileBytes;
 constexpr int kNumBars = 2 * kStages + 8 + kCqSlots;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;         // +1024: manual 1 KB alignment
 
 struct MatchArgs {
   const int32_t* qn;   // [nq] |q|^2
-  const int32_t* cq;   // [n_tiles*128] packed per-row constants
+  const int32_t* cq;   // [n_tiles][132] packed per-row constants + chunk minima
   uint32_t* part_d2;   // [n_seg][nq][2]
   int32_t* part_idx;   // [n_seg][nq][2]
   int nq;
@@ -61,21 +69,43 @@ struct MatchArgs {
   int idx_base;
 };
 
-// One chunk of 32 accumulator columns -> running top-2 (straightforward 4 ops / element).
+// One chunk of 32 accumulator columns -> running top-2, in three levels of increasing cost:
+//  1. bound: every key of the chunk is >= (cmin - 2*max(acc)) << 8 where cmin is the smallest
+//     |t|^2 of the chunk; if that already exceeds the thread's 2nd best nothing can change
+//     (~0.5 ALU op per element: a 3-input max tree on the raw accumulators);
+//  2. exact: compute the 32 packed keys and their minimum (1 IMAD + 0.5 min3 per element);
+//  3. update: the plain running top-2 (3 ops per element) - after the first few thousand columns
+//     of a sweep only a few percent of the chunks get here.
+// All comparisons are exact, so pruning never changes the result.
 __device__ __forceinline__ void top2_chunk(const uint32_t (&v)[32], const int4* __restrict__ cq4,
-                                           int& m1, int& m2) {
+                                           int cmin, int& m1, int& m2, bool& touched) {
+#if SOD_EXP == 1 || SOD_EXP == 2
+  return;
+#endif
+  int amax = static_cast<int>(v[0]);
+#pragma unroll
+  for (int j = 1; j < 32; ++j) amax = max(amax, static_cast<int>(v[j]));
+  // (cmin - 2*amax) is in d2 units relative to |q|^2; m2 >> 8 is the same quantity of the 2nd best.
+  if (cmin - 2 * amax > (m2 >> 8)) return;
+  int k[32];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int4 c = cq4[j];
-    int k, t;
-    k = c.x - 512 * static_cast<int>(v[4 * j + 0]);
-    t = max(m1, k); m1 = min(m1, k); m2 = min(m2, t);
-    k = c.y - 512 * static_cast<int>(v[4 * j + 1]);
-    t = max(m1, k); m1 = min(m1, k); m2 = min(m2, t);
-    k = c.z - 512 * static_cast<int>(v[4 * j + 2]);
-    t = max(m1, k); m1 = min(m1, k); m2 = min(m2, t);
-    k = c.w - 512 * static_cast<int>(v[4 * j + 3]);
-    t = max(m1, k); m1 = min(m1, k); m2 = min(m2, t);
+    k[4 * j + 0] = c.x - 512 * static_cast<int>(v[4 * j + 0]);
+    k[4 * j + 1] = c.y - 512 * static_cast<int>(v[4 * j + 1]);
+    k[4 * j + 2] = c.z - 512 * static_cast<int>(v[4 * j + 2]);
+    k[4 * j + 3] = c.w - 512 * static_cast<int>(v[4 * j + 3]);
+  }
+  int kmin = k[0];
+#pragma unroll
+  for (int j = 1; j < 32; ++j) kmin = min(kmin, k[j]);
+  if (kmin >= m2) return;
+  touched = true;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int t = max(m1, k[j]);
+    m1 = min(m1, k[j]);
+    m2 = min(m2, t);
   }
 }
 
@@ -168,9 +198,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
           // step j happens after MMA(j-kStages) retired, hence after the epilogue finished step
           // j-kStages-2; steps j-kStages-1 .. j-1 may still be live -> kStages+2 slots suffice.
           const uint32_t slot = step % kCqSlots;
-          mbar_arrive_expect_tx(bar_cqfull(slot), kTileN * 4);
-          bulk_load_1d(base + kOffCq + slot * kTileN * 4, a.cq + static_cast<int64_t>(t) * kTileN,
-                       kTileN * 4, bar_cqfull(slot));
+          mbar_arrive_expect_tx(bar_cqfull(slot), kCqTileBytes);
+          bulk_load_1d(base + kOffCq + slot * kCqTileBytes, a.cq + static_cast<int64_t>(t) * kCqTile,
+                       kCqTileBytes, bar_cqfull(slot));
         }
       }
     }
@@ -220,7 +250,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
       const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
-      int m1 = INT_MAX, m2 = INT_MAX, i1 = -1, i2 = -1;
+      // Between tiles m1/m2 keep their column byte cleared: an equal distance in a later tile
+      // then never displaces an earlier one (lowest database index wins, as in cv2).
+      int m1 = kInitKey, m2 = kInitKey, i1 = -1, i2 = -1;
       for (int t = t0; t < t1; ++t, ++step) {
         const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
         const uint32_t slot = step % kCqSlots, cqph = (step / kCqSlots) & 1u;
@@ -228,35 +260,43 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait(bar_cqfull(slot), cqph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
-        const int4* cq4 = reinterpret_cast<const int4*>(smem + kOffCq + slot * kTileN * 4);
-        // Clear the column byte: an equal distance in this tile must not displace an earlier tile.
-        const int s1 = m1 & ~0xFF, s2 = m2 & ~0xFF;
-        m1 = s1;
-        m2 = s2;
+        const int4* cq4 = reinterpret_cast<const int4*>(smem + kOffCq + slot * kCqTileBytes);
+        const int4 cmin = cq4[kTileN / 4];  // per-chunk minima of |t|^2
+        const int s1 = m1, s2 = m2;
+        bool touched = false;
         uint32_t va[32], vb[32];
+#if SOD_EXP == 2
+        for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0;
+#define tmem_ld32(a, b)
+#define tmem_ld_wait_on(a)
+#endif
         tmem_ld32(taddr, va);
         tmem_ld_wait_on(va);
-        tmem_ld32(taddr + 32, vb);
-        top2_chunk(va, cq4, m1, m2);
+        tmem_ld32(taddr + kChunk, vb);
+        top2_chunk(va, cq4, cmin.x, m1, m2, touched);
         tmem_ld_wait_on(vb);
-        tmem_ld32(taddr + 64, va);
-        top2_chunk(vb, cq4 + 8, m1, m2);
+        tmem_ld32(taddr + 2 * kChunk, va);
+        top2_chunk(vb, cq4 + 8, cmin.y, m1, m2, touched);
         tmem_ld_wait_on(va);
-        tmem_ld32(taddr + 96, vb);
-        top2_chunk(va, cq4 + 16, m1, m2);
+        tmem_ld32(taddr + 3 * kChunk, vb);
+        top2_chunk(va, cq4 + 16, cmin.z, m1, m2, touched);
         tmem_ld_wait_on(vb);
         // Every TMEM read of this accumulator buffer has landed: hand it back to the MMA warp.
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(acc));
-        top2_chunk(vb, cq4 + 24, m1, m2);
-        // Recover database indices for entries that changed in this tile.
-        const int tile_base = a.idx_base + t * kTileN;
-        if (m1 != s1) {
-          i2 = (m2 == s1) ? i1 : tile_base + (m2 & 0xFF);
-          i1 = tile_base + (m1 & 0xFF);
-        } else if (m2 != s2) {
-          i2 = tile_base + (m2 & 0xFF);
+        top2_chunk(vb, cq4 + 24, cmin.w, m1, m2, touched);
+        if (touched) {
+          // Recover database indices of the entries that changed in this tile.
+          const int tile_base = a.idx_base + t * kTileN;
+          if (m1 != s1) {
+            i2 = (m2 == s1) ? i1 : tile_base + (m2 & 0xFF);
+            i1 = tile_base + (m1 & 0xFF);
+          } else if (m2 != s2) {
+            i2 = tile_base + (m2 & 0xFF);
+          }
+          m1 &= ~0xFF;
+          m2 &= ~0xFF;
         }
       }
       if (row < a.nq) {
@@ -276,23 +316,47 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: one warp per descriptor row, 4 bytes per lane, __dp4a for the squares.
-__global__ void row_sqnorm_kernel(const uint8_t* __restrict__ x, int64_t n_rows, int64_t n_out,
-                                  int32_t* __restrict__ out, int pack_cq) {
+// K1 (query side): one warp per descriptor row, 4 bytes per lane, __dp4a for the squares.
+__global__ void row_sqnorm_kernel(const uint8_t* __restrict__ x, int64_t n_rows,
+                                  int32_t* __restrict__ out) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= n_out) return;
-  if (row >= n_rows) {  // padding rows of cq: can never win a comparison
-    if (lane == 0) out[row] = INT_MAX;
-    return;
-  }
+  if (row >= n_rows) return;
   const uint32_t w = reinterpret_cast<const uint32_t*>(x + row * SOD_DESC_DIM)[lane];
   uint32_t s = __dp4a(w, w, 0u);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0)
-    out[row] = pack_cq ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(row & (kTileN - 1)))
-                       : static_cast<int32_t>(s);
+  if (lane == 0) out[row] = static_cast<int32_t>(s);
+}
+
+// K1 (database side): one CTA of 128 threads per tile of 128 rows, one row per thread (a full
+// 128-byte line each).  Writes the tile's 128 packed keys (|t|^2 << 8 | column; INT_MAX for rows
+// past the end, which can never win) and the minimum |t|^2 of each 32-row chunk.
+__global__ void __launch_bounds__(kTileN)
+db_prepare_kernel(const uint8_t* __restrict__ db, int64_t n_rows, int32_t* __restrict__ cq) {
+  const int64_t tile = blockIdx.x;
+  const int col = threadIdx.x;
+  const int64_t row = tile * kTileN + col;
+  int32_t key = INT_MAX, c = 0x3FFFFFFF;
+  if (row < n_rows) {
+    const uint4* p = reinterpret_cast<const uint4*>(db + row * SOD_DESC_DIM);
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SOD_DESC_DIM / 16; ++j) {
+      const uint4 w = __ldg(p + j);
+      s = __dp4a(w.x, w.x, s);
+      s = __dp4a(w.y, w.y, s);
+      s = __dp4a(w.z, w.z, s);
+      s = __dp4a(w.w, w.w, s);
+    }
+    c = static_cast<int32_t>(s);
+    key = static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col));
+  }
+  int32_t* out = cq + tile * kCqTile;
+  out[col] = key;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
+  if ((col & 31) == 0) out[kTileN + (col >> 5)] = c;
 }
 
 // K0: float32 -> u8 with an integrality check.
@@ -429,8 +493,8 @@ using namespace sod;
 
 extern "C" {
 
-int64_t sod_padded_rows(int64_t n_rows) {
-  return n_rows <= 0 ? 0 : (n_rows + kTileN - 1) / kTileN * kTileN;
+int64_t sod_cq_ints(int64_t n_rows) {
+  return n_rows <= 0 ? 0 : (n_rows + kTileN - 1) / kTileN * kCqTile;
 }
 
 int sod_pack_u8_from_f32(const float* src, int64_t n_rows, uint8_t* dst, int32_t* nonint_flag,
@@ -451,12 +515,11 @@ int sod_db_prepare(const uint8_t* db, int64_t n_rows, int32_t* cq, sod_stream_t 
   SOD_CHECK_ARG(n_rows >= 0 && n_rows < (int64_t(1) << 31) - kTileN, "n_rows out of range");
   if (n_rows == 0) return SOD_OK;
   SOD_CHECK_ARG(db && cq, "null pointer");
-  const int64_t n_out = sod_padded_rows(n_rows);
-  const int threads = 256;
-  const int64_t blocks = (n_out * 32 + threads - 1) / threads;
-  row_sqnorm_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      db, n_rows, n_out, cq, 1);
-  SOD_CHECK_LAUNCH("row_sqnorm_kernel(db)");
+  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(db) & 15) == 0, "db must be 16-byte aligned");
+  const int64_t tiles = (n_rows + kTileN - 1) / kTileN;
+  db_prepare_kernel<<<static_cast<unsigned>(tiles), kTileN, 0, static_cast<cudaStream_t>(stream)>>>(
+      db, n_rows, cq);
+  SOD_CHECK_LAUNCH("db_prepare_kernel");
   return SOD_OK;
 }
 
@@ -467,8 +530,8 @@ int sod_query_prepare(const uint8_t* q, int64_t n_rows, int32_t* qn, sod_stream_
   const int threads = 256;
   const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
   row_sqnorm_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      q, n_rows, n_rows, qn, 0);
-  SOD_CHECK_LAUNCH("row_sqnorm_kernel(query)");
+      q, n_rows, qn);
+  SOD_CHECK_LAUNCH("row_sqnorm_kernel");
   return SOD_OK;
 }
 

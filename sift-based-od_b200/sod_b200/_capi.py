@@ -5,9 +5,11 @@ There is no fallback: if the library is missing or cannot be loaded, importing t
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libsod_b200.so"
+# SOD_B200_LIB selects another build of the same library (kernel experiments); never a fallback.
+_LIB_PATH = Path(os.environ.get("SOD_B200_LIB") or Path(__file__).resolve().parent / "libsod_b200.so")
 
 SOD_OK = 0
 DESC_DIM = 128
@@ -36,7 +38,7 @@ _PROTOS = {
     "sod_version": (C.c_int, []),
     "sod_last_error": (C.c_char_p, []),
     "sod_device_sm_count": (C.c_int, []),
-    "sod_padded_rows": (_i64, [_i64]),
+    "sod_cq_ints": (_i64, [_i64]),
     "sod_pack_u8_from_f32": (C.c_int, [_p, _i64, _p, _p, _p]),
     "sod_db_prepare": (C.c_int, [_p, _i64, _p, _p]),
     "sod_query_prepare": (C.c_int, [_p, _i64, _p, _p]),

@@ -71,7 +71,7 @@ class DescriptorShard:
 def prepare_db(des_u8: torch.Tensor, index_base: int = 0) -> DescriptorShard:
     des_u8 = _require_cuda(des_u8, torch.uint8, "database descriptors")
     n = int(des_u8.shape[0])
-    cq = torch.empty(max(int(lib.sod_padded_rows(n)), 1), dtype=torch.int32, device=des_u8.device)
+    cq = torch.empty(max(int(lib.sod_cq_ints(n)), 1), dtype=torch.int32, device=des_u8.device)
     check(lib.sod_db_prepare(_ptr(des_u8), n, _ptr(cq), _stream()), "sod_db_prepare")
     return DescriptorShard(des_u8, cq, int(index_base))
 

@@ -1,0 +1,53 @@
+"""Dev tool: time sod_match_top2 alone on device-resident inputs (CUDA events)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+from sod_b200 import engine as E  # noqa: E402
+
+
+def sift_like_gpu(n, g):
+    x = torch.randn((n, 128), device="cuda", generator=g).abs_()
+    x /= x.norm(dim=1, keepdim=True)
+    x.clamp_(max=0.2)
+    x /= x.norm(dim=1, keepdim=True)
+    return (x * 512).round_().clamp_(0, 255).to(torch.uint8)
+
+
+def run(nq, ndb, iters=10, kind="uniform"):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    if kind == "uniform":
+        q = torch.randint(0, 256, (nq, 128), dtype=torch.uint8, device="cuda", generator=g)
+        db = torch.randint(0, 256, (ndb, 128), dtype=torch.uint8, device="cuda", generator=g)
+    else:
+        q, db = sift_like_gpu(nq, g), sift_like_gpu(ndb, g)
+    m = E.Matcher(E.prepare_db(db))
+    for _ in range(3):
+        m.top2(q)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        m.top2(q)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
+    ms = float(np.median(ts))
+    ops = 2.0 * nq * ndb * 128
+    print(f"{kind:>8} nq={nq:>8} ndb={ndb:>8}  {ms:9.3f} ms (min {min(ts):.3f})  {ops / ms / 1e9:8.1f} TOPS  "
+          f"{nq / ms * 1e3 / 1e6:8.3f} Mq/s", flush=True)
+
+
+if __name__ == "__main__":
+    shapes = [(10000, 100000), (10000, 1000000), (65536, 1000000)]
+    if len(sys.argv) > 1:
+        shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
+    kinds = os.environ.get("SOD_BENCH_KINDS", "uniform,sift").split(",")
+    for kind in kinds:
+        for nq, ndb in shapes:
+            run(nq, ndb, kind=kind)
