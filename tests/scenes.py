@@ -50,13 +50,17 @@ class SyntheticScene:
 def make_scene(seed: int, n_images: int = 1, kp_per_image: int = 3000, n_query: int = 800,
                n_true: int = 200, width: int = 2000, height: int = 1500, model_w: int = 1500,
                model_h: int = 1000, scales=(0.5,), noise_px: float = 1.5, desc_noise: int = 3,
-               n_dup: int = 0) -> SyntheticScene:
+               n_dup: int = 0, n_false: int = 0, jitter_frac: float = 0.0,
+               jitter_px: float = 40.0) -> SyntheticScene:
     """A query image containing one instance of each of the first len(scales) model images.
 
     Instance i is model image i mapped by a similarity (scale scales[i] = 2^k, random rotation and
     translation) plus N(0, noise_px) jitter; octaves are chosen so that 2^(q_oct - m_oct) equals the
     scale, angles rotate with the object, descriptors are the model's plus integer noise.  The rest
-    of the query keypoints are clutter.  n_dup model rows are duplicated to create exact ties.
+    of the query keypoints are clutter.  n_dup model rows are duplicated to create exact ties;
+    n_false clutter keypoints get the descriptor of a random model row (they pass the ratio test
+    but vote at random poses); a fraction jitter_frac of the planted matches is displaced by
+    N(0, jitter_px) so that the affine stage has outliers to remove.
     """
     rng = np.random.default_rng(seed)
     ndb = n_images * kp_per_image
@@ -103,11 +107,20 @@ def make_scene(seed: int, n_images: int = 1, kp_per_image: int = 3000, n_query: 
         rot = np.stack([math.cos(th) * rel[:, 0] - math.sin(th) * rel[:, 1],
                         math.sin(th) * rel[:, 0] + math.cos(th) * rel[:, 1]], 1)
         qi = true_q[sl]
-        q_xy[qi] = (rot + c_q + rng.normal(0, noise_px, rot.shape)).astype(np.float32)
+        jit = rng.normal(0, noise_px, rot.shape)
+        far = rng.random(len(t)) < jitter_frac
+        jit[far] = rng.normal(0, jitter_px, (int(far.sum()), 2))
+        q_xy[qi] = (rot + c_q + jit).astype(np.float32)
         q_angle[qi] = np.mod(m_angle[t].astype(np.float64) + math.degrees(th), 360.0).astype(np.float32)
         q_angle[qi] = np.where(q_angle[qi] >= 360.0, 0.0, q_angle[qi])
         q_oct[qi] = m_oct[t] + k          # scale_factor = 2^(q_oct - m_oct) = s
         q_des[qi] = np.clip(m_des[t].astype(np.int16) + rng.integers(-desc_noise, desc_noise + 1, (len(t), 128)),
+                            0, 255).astype(np.uint8)
+    if n_false:
+        free = np.setdiff1d(np.arange(n_query), true_q)
+        fq = rng.choice(free, n_false, replace=False)
+        ft = rng.integers(0, ndb, n_false)
+        q_des[fq] = np.clip(m_des[ft].astype(np.int16) + rng.integers(-desc_noise, desc_noise + 1, (n_false, 128)),
                             0, 255).astype(np.uint8)
     return SyntheticScene(
         m_des=m_des, m_xy=m_xy, m_angle=m_angle, m_octave=pack_octave(m_oct, m_layer),

@@ -1,0 +1,104 @@
+"""The oracle (oracle/sod_oracle.py) held to outputs of the real reference (tests/golden/*.npz,
+made by tests/golden/make_golden.py from /root/reference).  CPU only."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import sod_oracle as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+SCENES = ["scene_single", "scene_multi", "scene_tiny"]
+
+
+def load(name):
+    z = np.load(GOLD / f"{name}.npz")
+    scene = O.Scene(z["in_q_xy"], z["in_q_angle"], z["in_q_octave"], z["in_m_xy"], z["in_m_angle"],
+                    z["in_m_octave"], z["in_m_image"], z["in_img_centroid"], z["in_img_size"],
+                    int(z["in_width"]), int(z["in_height"]))
+    return z, scene
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_matching_equals_cv2_knnmatch(name):
+    z, _ = load(name)
+    idx, d2 = O.knn2(z["in_q_des"], z["in_m_des"])
+    np.testing.assert_array_equal(idx, z["knn_idx"])
+    np.testing.assert_array_equal(O.match_distance(d2), z["knn_dist"])       # float32, bit-exact
+    ok = O.ratio_pass(d2, idx)
+    np.testing.assert_array_equal(np.nonzero(ok)[0], z["match_q"])
+    np.testing.assert_array_equal(idx[ok, 0], z["match_t"])
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_hough_dict_equals_reference(name):
+    z, scene = load(name)
+    table = O.hough_vote(scene, z["match_q"], z["match_t"], int(z["bins"]))
+    keys = np.array([k[1:] for k in table.keys()], np.int32).reshape(-1, 4)
+    np.testing.assert_array_equal(keys, z["bin_keys"])                       # same insertion order
+    bins = list(table.values())
+    np.testing.assert_array_equal([b.votes for b in bins], z["bin_votes"])
+    means = np.array([[b.centroid[0], b.centroid[1], b.angle, b.scale, b.img_size[0], b.img_size[1]]
+                      for b in bins])
+    np.testing.assert_array_equal(means, z["bin_means"])                     # float64, bit-exact
+    off = z["bin_mem_off"]
+    for i, b in enumerate(bins):
+        pairs = z["bin_mem"][off[i]:off[i + 1]]
+        np.testing.assert_array_equal(z["match_q"][b.members], pairs[:, 0])
+        np.testing.assert_array_equal(z["match_t"][b.members], pairs[:, 1])
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_vectorized_bins_equal_reference(name):
+    z, scene = load(name)
+    _, base = O.hough_base_bins_vectorized(scene, z["match_q"], z["match_t"], int(z["bins"]))
+    keys, counts = O.vote_counts_vectorized(base, np.zeros(len(base), np.int32), int(z["bins"]))
+    b = int(z["bins"])
+    gk = ((z["bin_keys"][:, 0].astype(np.int64) * b + z["bin_keys"][:, 1]) * b + z["bin_keys"][:, 2]) * b + z["bin_keys"][:, 3]
+    order = np.argsort(gk)
+    np.testing.assert_array_equal(keys, gk[order])
+    np.testing.assert_array_equal(counts, z["bin_votes"][order])
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_affine_verification_equals_reference(name):
+    z, scene = load(name)
+    table = O.hough_vote(scene, z["match_q"], z["match_t"], int(z["bins"]))
+    vb = O.valid_bins(table, int(z["vote_thr"]))
+    np.testing.assert_array_equal(np.array([b.pose for b in vb], np.int32).reshape(-1, 4), z["valid_keys"])
+    live = O.affine_verify(scene, z["match_q"], z["match_t"], vb, int(z["affine_thr"]))
+    np.testing.assert_array_equal(np.array([b.pose for b in live], np.int32).reshape(-1, 4), z["live_keys"])
+    np.testing.assert_array_equal([b.votes for b in live], z["live_votes"])
+    np.testing.assert_array_equal(np.array([b.affine for b in live]).reshape(-1, 6), z["live_params"])
+    off = z["live_mem_off"]
+    for i, b in enumerate(live):
+        pairs = z["live_mem"][off[i]:off[i + 1]]
+        np.testing.assert_array_equal(z["match_q"][b.members], pairs[:, 0])
+        np.testing.assert_array_equal(z["match_t"][b.members], pairs[:, 1])
+    assert sum(b.votes for b in live) == int(z["n_pairs_after"])
+
+
+def test_known_answers():
+    z = np.load(GOLD / "kat.npz")
+    lut = O.sigma_lut(15, int(z["sigma_k"][0]), int(z["sigma_k"][-1]))
+    np.testing.assert_array_equal(lut, z["sigma_bin15"])
+    np.testing.assert_array_equal(O.ratio_pass(z["ratio_d2"]), z["ratio_pass"])
+    assert O.ratio_pass(np.array([[18, 32]]))[0]
+
+
+def test_ties_lowest_index_first():
+    rng = np.random.default_rng(3)
+    db = rng.integers(0, 256, (50, 128), dtype=np.uint8)
+    q = db[[7]].copy()
+    db[30] = db[40] = db[7]
+    idx, d2 = O.knn2(q, db)
+    assert idx.tolist() == [[7, 30]] and d2.tolist() == [[0, 0]]
+
+
+def test_degenerate_sizes():
+    q = np.zeros((3, 128), np.uint8)
+    idx, d2 = O.knn2(q, np.zeros((0, 128), np.uint8))
+    assert (idx == -1).all()
+    idx, d2 = O.knn2(q, np.ones((1, 128), np.uint8))
+    assert idx.tolist() == [[0, -1]] * 3 and d2[:, 0].tolist() == [128] * 3
+    assert not O.ratio_pass(d2, idx).any()
