@@ -82,6 +82,103 @@ int sod_top2_merge(const int32_t* parts_idx, const uint32_t* parts_d2, int32_t n
                    int64_t n_query, int32_t* out_idx, uint32_t* out_d2, float* out_dist,
                    uint8_t* out_pass, double ratio, sod_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Hough voting and affine verification
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Keypoints as structure-of-arrays: exactly the fields the path reads from cv2.KeyPoint
+ * (.pt, .angle, .octave). */
+typedef struct {
+  const float* xy;       /* [n][2] KeyPoint.pt */
+  const float* angle;    /* [n] KeyPoint.angle, degrees in [0,360) */
+  const int32_t* octave; /* [n] KeyPoint.octave as packed by OpenCV SIFT (low byte = octave) */
+  int64_t n;
+} sod_keypoints;
+
+/* Everything Main holds about the query image(s) and the model database that the Hough and affine
+ * stages read (main.py:20-28).  A "frame" is one query image; a "group" is one Hough space.
+ * The reference has one frame and one space for all model images (groups_per_frame = 1,
+ * image_group = NULL); multi-object configurations give every object its own space. */
+typedef struct {
+  sod_keypoints query;          /* kp_query (all frames concatenated) */
+  const int32_t* query_frame;   /* [query.n] frame of each query keypoint; NULL = all frame 0 */
+  const int32_t* frame_wh;      /* [n_frames][2] (W,H) of each query image (image_query_size) */
+  int32_t n_frames;
+  sod_keypoints model;          /* kp (whole database, indexed by global descriptor row) */
+  const int32_t* model_image;   /* [model.n] model image each keypoint came from */
+  const double* image_centroid; /* [n_images][2] img_centroid_list entries */
+  const double* image_size;     /* [n_images][2] (w,h) img_size_list entries */
+  const int32_t* image_group;   /* [n_images] Hough space of the image inside a frame; NULL = 0 */
+  int32_t n_images;
+  int32_t groups_per_frame;
+} sod_scene;
+
+#define SOD_SIGMA_LUT_MIN (-24)
+#define SOD_SIGMA_LUT_LEN 49
+#define SOD_MAX_BINS 15 /* bins^4 uint32 counters must fit one SM's shared memory */
+
+/* Outputs of sod_hough_vote (device).  Bin records are compact and in no particular order;
+ * `bin_order` reproduces the reference's dict insertion order when sorted ascending. */
+typedef struct {
+  double* pose;        /* [M][4] x, y, alpha, scale per match (estimate_object_pose) */
+  uint32_t* base_bin;  /* [M] ix | iy<<8 | itheta<<16 | isigma<<24 (calculate_bin_index) */
+  uint8_t* near_edge;  /* [M] 1 if x, y or theta lies within 1e-9 of a bin boundary */
+  int32_t* counters;   /* [4] n_bins, n_votes, n_near_edge, overflow flag; zeroed by the call */
+  int32_t* bin_group;  /* [cap_bins] frame * groups_per_frame + image_group */
+  int32_t* bin_code;   /* [cap_bins] ((ix*bins + iy)*bins + itheta)*bins + isigma */
+  int32_t* bin_count;  /* [cap_bins] votes */
+  int32_t* bin_offset; /* [cap_bins] start of the bin's members */
+  int64_t* bin_order;  /* [cap_bins] first member * 16 + its vote offset (w*8+x*4+y*2+z) */
+  double* bin_mean;    /* [cap_bins][6] running means cx, cy, angle, scale, img_w, img_h (PoseBin) */
+  int32_t* members;    /* [cap_votes] match ids, ascending inside every bin */
+  int64_t cap_bins;    /* 16*M always suffices */
+  int64_t cap_votes;
+} sod_hough_out;
+
+/* Stable compaction of the ratio survivors: match_q = query rows with pass != 0 in ascending
+ * order, match_t = their nearest database row (main.py:81-86 builds the same list).  n_out is a
+ * device int32.  scratch: sod_compact_scratch_bytes(n_query). */
+size_t sod_compact_scratch_bytes(int64_t n_query);
+int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t* match_q,
+                        int32_t* match_t, int32_t* n_out, void* scratch, sod_stream_t stream);
+
+/* Bytes of scratch for sod_hough_vote. */
+size_t sod_hough_workspace_bytes(int64_t n_matches, int64_t n_groups);
+
+/* K4.  Main.apply_hough_transform (main.py:89-119) with estimate_object_pose and
+ * calculate_bin_index (HoughTransformHelperFunctions.py:4-72) and the PoseBin bookkeeping
+ * (PoseBin.py:19-54): every match votes into the <=16 bins (ix+w, iy+x, itheta+y, isigma+z) whose
+ * coordinates are all < bins.  n_matches is the capacity of match_q/match_t; if n_matches_dev is
+ * not NULL the actual count is read from it on the device.  sigma_lut[k - SOD_SIGMA_LUT_MIN] is
+ * the isigma of scale factor 2^k (device int32[SOD_SIGMA_LUT_LEN]). */
+int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                   int64_t n_matches, const int32_t* n_matches_dev, int32_t bins,
+                   const int32_t* sigma_lut, const sod_hough_out* out, void* workspace,
+                   size_t workspace_bytes, sod_stream_t stream);
+
+/* Outputs of sod_affine_verify (device), one entry per bin that entered with >= vote_threshold. */
+typedef struct {
+  int32_t* counters;    /* [2] n_valid, overflow; zeroed by the call */
+  int32_t* valid_bin;   /* [cap_valid] index of the bin record */
+  double* params;       /* [cap_valid][6] m1 m2 m3 m4 tx ty of the last fit */
+  int32_t* votes;       /* [cap_valid] members left */
+  int32_t* status;      /* [cap_valid] bit0 live (votes >= affine_threshold at the fixed point),
+                           bit1 near-singular normal matrix, bits 8.. number of passes */
+  uint8_t* member_keep; /* [cap_votes] aligned with sod_hough_out.members: 1 = still in its bin */
+  int64_t cap_valid;
+} sod_affine_out;
+
+/* K5.  Main.get_valid_bins + Main.apply_affine_parameters (main.py:121-157) with AffineParameters
+ * and remove_outliers (AffineParameters.py:89-160): per bin, fit u = m1 x + m2 y + tx,
+ * v = m3 x + m4 y + ty by the pseudo-inverse of the normal matrix (rcond 1e-15), drop pairs whose
+ * residual exceeds W*isigma/factor or H*isigma/factor, repeat until nothing is dropped or fewer than
+ * affine_threshold pairs remain. */
+int sod_affine_verify(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                      const sod_hough_out* hough, int32_t bins, int32_t vote_threshold,
+                      int32_t affine_threshold, double factor, const sod_affine_out* out,
+                      sod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

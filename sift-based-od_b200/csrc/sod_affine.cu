@@ -1,0 +1,213 @@
+// K5: valid-bin selection and per-bin affine verification.
+//
+// Replaces Main.get_valid_bins / Main.apply_affine_parameters (main.py:121-157), AffineParameters
+// (AffineParameters.py:89-113: Gen_A, Gen_b, Calc_x) and remove_outliers (AffineParameters.py:116-160).
+//
+// The reference's global "while anything changed" loop over all bins is, bin by bin, an independent
+// fixed-point iteration (fit and residual test only read the bin's own pairs),
+// so one warp owns one bin for all its passes.  The 6x6 normal matrix A^T A of the reference
+// (parameter order m1 m2 m3 m4 tx ty) is two interleaved copies of the 3x3 matrix
+//   S = sum [x y 1]^T [x y 1]
+// so pinv(A^T A) A^T b = ( pinv(S) sum [x y 1]^T u , pinv(S) sum [x y 1]^T v ).  pinv(S) comes from a
+// Jacobi eigen-decomposition in fp64 with numpy's default cut-off (rcond = 1e-15 x largest
+// eigenvalue), which reproduces the minimum-norm answer on rank-deficient bins.
+#include "sod_common.cuh"
+
+namespace sod {
+namespace {
+
+struct AffineArgs {
+  sod_scene sc;
+  const int32_t* match_q;
+  const int32_t* match_t;
+  const int32_t* hough_counters;
+  const int32_t* bin_group;
+  const int32_t* bin_code;
+  const int32_t* bin_count;
+  const int32_t* bin_offset;
+  const int32_t* members;
+  int64_t cap_bins;
+  int bins, vote_threshold, affine_threshold;
+  double factor;
+  sod_affine_out out;
+};
+
+__global__ void affine_select_kernel(const AffineArgs a) {
+  int64_t n_bins = a.hough_counters[0];
+  if (n_bins > a.cap_bins || a.hough_counters[3]) n_bins = 0;
+  for (int64_t rec = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; rec < n_bins;
+       rec += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (a.bin_count[rec] < a.vote_threshold) continue;
+    const int v = atomicAdd(&a.out.counters[0], 1);
+    if (v < a.out.cap_valid)
+      a.out.valid_bin[v] = static_cast<int32_t>(rec);
+    else
+      a.out.counters[1] = 1;
+  }
+}
+
+// Cyclic Jacobi on a symmetric 3x3: A -> diag(w), columns of V are the eigenvectors.
+__device__ void jacobi3(double (&A)[3][3], double (&V)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 16; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+    if (off <= 1e-300 || off <= 1e-22 * diag) break;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      const double apq = A[p][q];
+      if (apq == 0.0) continue;
+      const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      const int r = 3 - p - q;  // the untouched index
+      const double app = A[p][p], aqq = A[q][q], arp = A[r][p], arq = A[r][q];
+      A[p][p] = app - t * apq;
+      A[q][q] = aqq + t * apq;
+      A[p][q] = A[q][p] = 0.0;
+      A[r][p] = A[p][r] = c * arp - s * arq;
+      A[r][q] = A[q][r] = s * arp + c * arq;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double vip = V[i][p], viq = V[i][q];
+        V[i][p] = c * vip - s * viq;
+        V[i][q] = s * vip + c * viq;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void affine_verify_kernel(const AffineArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  int64_t n_valid = a.out.counters[0];
+  if (n_valid > a.out.cap_valid) n_valid = a.out.cap_valid;
+  const float2* mxy = reinterpret_cast<const float2*>(a.sc.model.xy);
+  const float2* qxy = reinterpret_cast<const float2*>(a.sc.query.xy);
+  for (int64_t v = warp; v < n_valid; v += n_warps) {
+    const int rec = a.out.valid_bin[v];
+    const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
+    const int frame = a.bin_group[rec] / a.sc.groups_per_frame;
+    const int isigma = a.bin_code[rec] % a.bins;
+    // remove_outliers thresholds use pose[3], the sigma BIN INDEX (AffineParameters.py:120-121)
+    const double x_ref = __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame] * isigma), a.factor);
+    const double y_ref = __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor);
+    uint8_t* keep = a.out.member_keep + off;
+    const int32_t* mem = a.members + off;
+    for (int j = lane; j < cnt; j += 32) keep[j] = 1;
+    __syncwarp();
+    int alive = cnt, passes = 0, live = 0, singular = 0;
+    double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
+    while (true) {
+      double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0, sn = 0;
+      double sxu = 0, syu = 0, su = 0, sxv = 0, syv = 0, sv = 0;
+      for (int j = lane; j < cnt; j += 32) {
+        if (!keep[j]) continue;
+        const int m = mem[j];
+        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+        const double x = pm.x, y = pm.y, u = pq.x, w = pq.y;
+        sxx += x * x; sxy += x * y; sx += x; syy += y * y; sy += y; sn += 1.0;
+        sxu += x * u; syu += y * u; su += u; sxv += x * w; syv += y * w; sv += w;
+      }
+      sxx = warp_sum(sxx); sxy = warp_sum(sxy); sx = warp_sum(sx); syy = warp_sum(syy);
+      sy = warp_sum(sy); sn = warp_sum(sn); sxu = warp_sum(sxu); syu = warp_sum(syu);
+      su = warp_sum(su); sxv = warp_sum(sxv); syv = warp_sum(syv); sv = warp_sum(sv);
+      double A[3][3] = {{sxx, sxy, sx}, {sxy, syy, sy}, {sx, sy, sn}};
+      double V[3][3];
+      jacobi3(A, V);
+      const double w0 = A[0][0], w1 = A[1][1], w2 = A[2][2];
+      const double wmax = fmax(fabs(w0), fmax(fabs(w1), fabs(w2)));
+      const double wmin = fmin(fabs(w0), fmin(fabs(w1), fabs(w2)));
+      const double cut = 1e-15 * wmax;  // numpy.linalg.pinv default rcond
+      if (wmin <= 1e-10 * wmax) singular = 1;
+      const double ru[3] = {sxu, syu, su}, rv[3] = {sxv, syv, sv};
+      const double wv[3] = {w0, w1, w2};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pu[i] = pv[i] = 0.0;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        if (!(fabs(wv[e]) > cut)) continue;
+        const double du = (V[0][e] * ru[0] + V[1][e] * ru[1] + V[2][e] * ru[2]) / wv[e];
+        const double dv = (V[0][e] * rv[0] + V[1][e] * rv[1] + V[2][e] * rv[2]) / wv[e];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          pu[i] += V[i][e] * du;
+          pv[i] += V[i][e] * dv;
+        }
+      }
+      int removed = 0;
+      for (int j = lane; j < cnt; j += 32) {
+        if (!keep[j]) continue;
+        const int m = mem[j];
+        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+        const double x = pm.x, y = pm.y;
+        const double ua = __dadd_rn(__dadd_rn(__dmul_rn(pu[0], x), __dmul_rn(pu[1], y)), pu[2]);
+        const double va = __dadd_rn(__dadd_rn(__dmul_rn(pv[0], x), __dmul_rn(pv[1], y)), pv[2]);
+        if (fabs(ua - static_cast<double>(pq.x)) > x_ref || fabs(va - static_cast<double>(pq.y)) > y_ref) {
+          keep[j] = 0;
+          ++removed;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+      __syncwarp();
+      alive -= removed;
+      ++passes;
+      if (alive < a.affine_threshold) break;  // dropped from valid_bins after this pass
+      if (removed == 0) { live = 1; break; }
+    }
+    if (lane == 0) {
+      double* p = a.out.params + v * 6;
+      p[0] = pu[0]; p[1] = pu[1]; p[2] = pv[0]; p[3] = pv[1]; p[4] = pu[2]; p[5] = pv[2];
+      a.out.votes[v] = alive;
+      a.out.status[v] = live | (singular << 1) | (passes << 8);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace sod
+
+using namespace sod;
+
+extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                                 const sod_hough_out* hough, int32_t bins, int32_t vote_threshold,
+                                 int32_t affine_threshold, double factor, const sod_affine_out* out,
+                                 sod_stream_t stream) {
+  SOD_CHECK_ARG(scene && hough && out, "null scene/hough/out");
+  SOD_CHECK_ARG(out->counters && out->valid_bin && out->params && out->votes && out->status &&
+                    out->member_keep && out->cap_valid > 0,
+                "null output array");
+  SOD_CHECK_ARG(bins >= 1 && bins <= SOD_MAX_BINS, "bins out of range");
+  SOD_CHECK_ARG(factor > 0, "factor must be positive");
+  SOD_CHECK_ARG(match_q && match_t && hough->counters && hough->bin_group && hough->bin_code &&
+                    hough->bin_count && hough->bin_offset && hough->members,
+                "null input array");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SOD_CHECK_CUDA(cudaMemsetAsync(out->counters, 0, 2 * sizeof(int32_t), st));
+  const int sms = device_sm_count();
+  if (sms <= 0) return SOD_ERR_CUDA;
+  AffineArgs a;
+  a.sc = *scene;
+  a.match_q = match_q; a.match_t = match_t; a.hough_counters = hough->counters;
+  a.bin_group = hough->bin_group; a.bin_code = hough->bin_code; a.bin_count = hough->bin_count;
+  a.bin_offset = hough->bin_offset; a.members = hough->members; a.cap_bins = hough->cap_bins;
+  a.bins = bins; a.vote_threshold = vote_threshold; a.affine_threshold = affine_threshold;
+  a.factor = factor; a.out = *out;
+  affine_select_kernel<<<sms * 4, 256, 0, st>>>(a);
+  SOD_CHECK_LAUNCH("affine_select_kernel");
+  affine_verify_kernel<<<sms * 8, 128, 0, st>>>(a);
+  SOD_CHECK_LAUNCH("affine_verify_kernel");
+  return SOD_OK;
+}

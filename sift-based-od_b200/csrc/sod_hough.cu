@@ -1,0 +1,544 @@
+// K4: generalized Hough voting (pose estimate, bin index, 16 votes per match, PoseBin bookkeeping)
+// and the stable compaction of ratio survivors that feeds it.
+//
+// Replaces Main.apply_hough_transform (main.py:89-119), estimate_object_pose / calculate_bin_index
+// (HoughTransformHelperFunctions.py:4-72), unpack_sift_octave (SiftHelperFunctions.py:25-40) and
+// PoseBin.update_posebin (PoseBin.py:19-54).
+//
+// Data flow (all on the caller's stream, no host synchronisation):
+//   pose    one thread per match: fp64 pose with the reference's operation order (explicit
+//           round-to-nearest intrinsics, no FMA contraction), base bin, Hough-space (group) id
+//   group   counting sort of the matches by group
+//   vote    one CTA per group at a time: a bins^4 uint32 histogram privatised in shared memory
+//           (202.5 KB at bins = 15) takes the <=16 votes of every match with shared-memory atomics;
+//           the vote that finds a zero counter owns ("creates") the bin and later emits its compact
+//           record, so the cost is proportional to the votes, not to the 50,625 bins
+//   finish  one warp per bin record: members sorted by match id (= reference append order), running
+//           means by the reference's sequential recurrence, insertion-order key
+#include <climits>
+
+#include "sod_common.cuh"
+
+namespace sod {
+namespace {
+
+constexpr double kPi = 3.141592653589793;           // math.pi
+constexpr double kTwoPi = 2.0 * 3.141592653589793;  // 2*math.pi (exact doubling)
+constexpr double kDegToRad = 3.141592653589793 / 180.0;  // CPython's math.radians multiplier
+constexpr int kVoteThreads = 1024;
+
+__device__ __forceinline__ int sext8(int v) {
+  const int o = v & 0xFF;
+  return o >= 128 ? o - 256 : o;
+}
+
+// Near a truncation boundary?  cos/sin on the device may differ from the host libm in the last
+// bit; only values this close to an integer could then land in another bin.
+__device__ __forceinline__ bool near_integer(double f) {
+  const double r = rint(f);
+  return fabs(f - r) <= 1e-9 * fmax(1.0, fabs(f));
+}
+
+struct PoseArgs {
+  sod_scene sc;
+  const int32_t* match_q;
+  const int32_t* match_t;
+  const int32_t* n_dev;
+  int64_t n_cap;
+  int bins;
+  const int32_t* sigma_lut;
+  double* pose;
+  uint32_t* base_bin;
+  uint8_t* near_edge;
+  int32_t* counters;
+  int32_t* group_of;
+  int32_t* group_count;
+};
+
+__device__ __forceinline__ int64_t live_count(const int32_t* n_dev, int64_t cap) {
+  if (!n_dev) return cap;
+  const int64_t n = *n_dev;
+  return n < cap ? n : cap;
+}
+
+__global__ void hough_pose_kernel(const PoseArgs a) {
+  const int64_t n = live_count(a.n_dev, a.n_cap);
+  const int bins = a.bins;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int qi = a.match_q[i], ti = a.match_t[i];
+    const float2 qp = reinterpret_cast<const float2*>(a.sc.query.xy)[qi];
+    const float2 mp = reinterpret_cast<const float2*>(a.sc.model.xy)[ti];
+    const int frame = a.sc.query_frame ? a.sc.query_frame[qi] : 0;
+    const double W = a.sc.frame_wh[2 * frame], H = a.sc.frame_wh[2 * frame + 1];
+    const int img = a.sc.model_image[ti];
+    const int grp = frame * a.sc.groups_per_frame + (a.sc.image_group ? a.sc.image_group[img] : 0);
+    const double cx = a.sc.image_centroid[2 * img], cy = a.sc.image_centroid[2 * img + 1];
+    // scale_factor = m_scale / q_scale = 2^(q_octave - m_octave), exact
+    const int k = sext8(a.sc.query.octave[qi]) - sext8(a.sc.model.octave[ti]);
+    const double s = ldexp(1.0, k);
+    const double tx = __dmul_rn(__dsub_rn(cx, static_cast<double>(mp.x)), s);
+    const double ty = __dmul_rn(__dsub_rn(cy, static_cast<double>(mp.y)), s);
+    double al = __dmul_rn(__dsub_rn(static_cast<double>(a.sc.query.angle[qi]),
+                                    static_cast<double>(a.sc.model.angle[ti])), kDegToRad);
+    al = fmod(__dadd_rn(al, kTwoPi), kTwoPi);  // operand is > 0: Python's % equals fmod here
+    if (al < 0.0) al = __dadd_rn(al, kTwoPi);
+    const double ca = cos(al), sa = sin(al);
+    const double rx = __dsub_rn(__dmul_rn(ca, tx), __dmul_rn(sa, ty));
+    const double ry = __dadd_rn(__dmul_rn(sa, tx), __dmul_rn(ca, ty));
+    const double x = __dadd_rn(rx, static_cast<double>(qp.x));
+    const double y = __dadd_rn(ry, static_cast<double>(qp.y));
+    double* po = a.pose + i * 4;
+    po[0] = x; po[1] = y; po[2] = al; po[3] = s;
+
+    const double fx = __ddiv_rn(__dmul_rn(x, static_cast<double>(bins)), W);
+    const double fy = __ddiv_rn(__dmul_rn(y, static_cast<double>(bins)), H);
+    const double ft = fmod(__ddiv_rn(__dmul_rn(al, static_cast<double>(bins)), kTwoPi),
+                           static_cast<double>(bins));
+    // int() truncates toward zero; clamp before converting so huge poses stay defined
+    int ix = static_cast<int>(fmin(fmax(trunc(fx), -1.0e6), 1.0e6));
+    int iy = static_cast<int>(fmin(fmax(trunc(fy), -1.0e6), 1.0e6));
+    ix = min(max(0, ix - 1), bins - 1);
+    iy = min(max(0, iy - 1), bins - 1);
+    const int it = static_cast<int>(ft);
+    const int kk = min(max(k, SOD_SIGMA_LUT_MIN), SOD_SIGMA_LUT_MIN + SOD_SIGMA_LUT_LEN - 1);
+    const int is = a.sigma_lut[kk - SOD_SIGMA_LUT_MIN];
+    a.base_bin[i] = static_cast<uint32_t>(ix) | (static_cast<uint32_t>(iy) << 8) |
+                    (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
+    const bool edge = near_integer(fx) || near_integer(fy) || near_integer(ft);
+    a.near_edge[i] = edge ? 1 : 0;
+    if (edge) atomicAdd(&a.counters[2], 1);
+    a.group_of[i] = grp;
+    atomicAdd(&a.group_count[grp], 1);
+  }
+}
+
+// Exclusive scan of n ints by one CTA (n is the number of Hough spaces: small).
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ in,
+                                                              int64_t n, int32_t* __restrict__ out,
+                                                              int32_t* __restrict__ out_copy,
+                                                              int32_t* __restrict__ total) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t v = i < n ? in[i] : 0;
+    int32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int32_t excl = carry + (warp ? warp_sums[warp - 1] : 0) + incl - v;
+    if (i < n) {
+      out[i] = excl;
+      if (out_copy) out_copy[i] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[n] = carry;
+    if (total) *total = carry;
+  }
+}
+
+__global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const int32_t* n_dev,
+                                     int64_t n_cap, int32_t* __restrict__ cursor,
+                                     int32_t* __restrict__ grouped) {
+  const int64_t n = live_count(n_dev, n_cap);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    grouped[atomicAdd(&cursor[group_of[i]], 1)] = static_cast<int32_t>(i);
+}
+
+struct VoteArgs {
+  const int32_t* group_off;  // [n_groups+1]
+  const int32_t* grouped;    // match ids grouped by Hough space
+  const uint32_t* base_bin;
+  uint16_t* creator;         // per grouped position: which of the 16 votes created its bin
+  int64_t n_groups;
+  int bins;
+  int32_t* counters;
+  int32_t* bin_group;
+  int32_t* bin_code;
+  int32_t* bin_count;
+  int32_t* bin_offset;
+  int32_t* members_raw;
+  int64_t cap_bins, cap_votes;
+};
+
+// Calls f(o, code) for each of the <=16 in-range votes of a match (main.py:105-110).
+template <class F>
+__device__ __forceinline__ void for_each_vote(uint32_t base, int bins, F&& f) {
+  const int ix = base & 0xFF, iy = (base >> 8) & 0xFF, it = (base >> 16) & 0xFF, is = base >> 24;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    const int cx = ix + ((o >> 3) & 1), cy = iy + ((o >> 2) & 1), ct = it + ((o >> 1) & 1),
+              cs = is + (o & 1);
+    if (cx < bins && cy < bins && ct < bins && cs < bins)
+      f(o, ((cx * bins + cy) * bins + ct) * bins + cs);
+  }
+}
+
+__global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteArgs a) {
+  extern __shared__ uint32_t hist[];  // bins^4 counters, all zero between groups
+  __shared__ int s_nbins, s_nvotes, s_rec_base, s_vote_base, s_rec_cur, s_vote_cur, s_ok;
+  const int bins = a.bins;
+  const int nb4 = bins * bins * bins * bins;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < nb4; i += kVoteThreads) hist[i] = 0;
+  __syncthreads();
+  for (int64_t g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+    const int beg = a.group_off[g], end = a.group_off[g + 1];
+    if (beg == end) continue;
+    if (tid == 0) s_nbins = s_nvotes = s_rec_cur = s_vote_cur = 0;
+    __syncthreads();
+    // A: count votes; remember which votes hit an empty counter.
+    int my_bins = 0, my_votes = 0;
+    for (int p = beg + tid; p < end; p += kVoteThreads) {
+      unsigned created = 0;
+      for_each_vote(a.base_bin[a.grouped[p]], bins, [&](int o, int code) {
+        if (atomicAdd(&hist[code], 1u) == 0u) created |= 1u << o;
+        ++my_votes;
+      });
+      a.creator[p] = static_cast<uint16_t>(created);
+      my_bins += __popc(created);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      my_bins += __shfl_xor_sync(0xffffffffu, my_bins, o);
+      my_votes += __shfl_xor_sync(0xffffffffu, my_votes, o);
+    }
+    if (lane == 0 && my_votes) {
+      atomicAdd(&s_nbins, my_bins);
+      atomicAdd(&s_nvotes, my_votes);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_rec_base = atomicAdd(&a.counters[0], s_nbins);
+      s_vote_base = atomicAdd(&a.counters[1], s_nvotes);
+      s_ok = (static_cast<int64_t>(s_rec_base) + s_nbins <= a.cap_bins) &&
+             (static_cast<int64_t>(s_vote_base) + s_nvotes <= a.cap_votes);
+      if (!s_ok) a.counters[3] = 1;
+    }
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    // B: the creating vote emits the bin record and turns the counter into a write cursor.
+    if (ok) {
+      for (int p = beg + tid; p < end; p += kVoteThreads) {
+        const unsigned created = a.creator[p];
+        if (!created) continue;
+        for_each_vote(a.base_bin[a.grouped[p]], bins, [&](int o, int code) {
+          if (!(created >> o & 1u)) return;
+          const int cnt = static_cast<int>(hist[code]);
+          const int rec = s_rec_base + atomicAdd(&s_rec_cur, 1);
+          const int off = s_vote_base + atomicAdd(&s_vote_cur, cnt);
+          a.bin_group[rec] = static_cast<int32_t>(g);
+          a.bin_code[rec] = code;
+          a.bin_count[rec] = cnt;
+          a.bin_offset[rec] = off;
+          hist[code] = static_cast<uint32_t>(off);
+        });
+      }
+    }
+    __syncthreads();
+    // C: every vote appends its match id to its bin.
+    if (ok) {
+      for (int p = beg + tid; p < end; p += kVoteThreads) {
+        const int m = a.grouped[p];
+        for_each_vote(a.base_bin[m], bins,
+                      [&](int, int code) { a.members_raw[atomicAdd(&hist[code], 1u)] = m; });
+      }
+    }
+    __syncthreads();
+    // D: creators clear their counters for the next group.
+    for (int p = beg + tid; p < end; p += kVoteThreads) {
+      const unsigned created = a.creator[p];
+      if (!created) continue;
+      for_each_vote(a.base_bin[a.grouped[p]], bins, [&](int o, int code) {
+        if (created >> o & 1u) hist[code] = 0u;
+      });
+    }
+    __syncthreads();
+  }
+}
+
+struct FinishArgs {
+  sod_scene sc;
+  const int32_t* match_t;
+  const double* pose;
+  const uint32_t* base_bin;
+  const int32_t* counters;
+  const int32_t* bin_code;
+  const int32_t* bin_count;
+  const int32_t* bin_offset;
+  const int32_t* members_raw;
+  int32_t* members;
+  int64_t* bin_order;
+  double* bin_mean;
+  int64_t cap_bins;
+  int bins;
+};
+
+// One warp per bin: rank-sort the members (ids are distinct), then lanes 0..5 each run one of the
+// six sequential running means of PoseBin.update_posebin: (old * votes + new) / (votes + 1).
+__global__ void hough_finish_kernel(const FinishArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  int64_t n_bins = a.counters[0];
+  if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
+  for (int64_t rec = warp; rec < n_bins; rec += n_warps) {
+    const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
+    const int32_t* raw = a.members_raw + off;
+    int32_t* out = a.members + off;
+    for (int i = lane; i < cnt; i += 32) {
+      const int32_t x = raw[i];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) rank += raw[j] < x;
+      out[rank] = x;
+    }
+    __syncwarp();
+    if (lane < 6) {
+      double mean = 0.0;
+      for (int j = 0; j < cnt; ++j) {
+        const int m = out[j];
+        double v;
+        if (lane < 4) {
+          v = a.pose[static_cast<int64_t>(m) * 4 + lane];
+        } else {
+          const int img = a.sc.model_image[a.match_t[m]];
+          v = a.sc.image_size[2 * img + (lane - 4)];
+        }
+        mean = j == 0 ? v
+                      : __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v),
+                                  static_cast<double>(j + 1));
+      }
+      a.bin_mean[rec * 6 + lane] = mean;
+    }
+    if (lane == 0) {
+      const int first = out[0];
+      const uint32_t base = a.base_bin[first];
+      int code = a.bin_code[rec];
+      const int b = a.bins;
+      const int cs = code % b; code /= b;
+      const int ct = code % b; code /= b;
+      const int cy = code % b; code /= b;
+      const int cx = code;
+      const int o = ((cx - static_cast<int>(base & 0xFF)) << 3) |
+                    ((cy - static_cast<int>((base >> 8) & 0xFF)) << 2) |
+                    ((ct - static_cast<int>((base >> 16) & 0xFF)) << 1) |
+                    (cs - static_cast<int>(base >> 24));
+      a.bin_order[rec] = static_cast<int64_t>(first) * 16 + o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ compaction
+constexpr int kCompactThreads = 1024;
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_count_kernel(const uint8_t* __restrict__ pass, int64_t n, int32_t* __restrict__ block_counts) {
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kCompactThreads + threadIdx.x;
+  const unsigned b = __ballot_sync(0xffffffffu, i < n && pass[i]);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s, __popc(b));
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ pass, int64_t n,
+                     const int32_t* __restrict__ block_off, int32_t* __restrict__ match_q,
+                     int32_t* __restrict__ match_t) {
+  __shared__ int warp_base[kCompactThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kCompactThreads + threadIdx.x;
+  const bool keep = i < n && pass[i];
+  const unsigned b = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_base[warp] = __popc(b);
+  __syncthreads();
+  if (warp == 0) {
+    int v = warp_base[lane], incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    warp_base[lane] = incl - v;
+  }
+  __syncthreads();
+  if (keep) {
+    const int pos = block_off[blockIdx.x] + warp_base[warp] + __popc(b & ((1u << lane) - 1u));
+    match_q[pos] = static_cast<int32_t>(i);
+    match_t[pos] = idx[i * 2];
+  }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+struct HoughWs {
+  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw;
+  uint16_t* creator;
+  size_t bytes;
+};
+
+HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes) {
+  HoughWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o += align256(bytes);
+    return p;
+  };
+  w.group_of = static_cast<int32_t*>(take(m * 4));
+  w.group_count = static_cast<int32_t*>(take((groups + 1) * 4));
+  w.group_off = static_cast<int32_t*>(take((groups + 1) * 4));
+  w.group_cursor = static_cast<int32_t*>(take((groups + 1) * 4));
+  w.grouped = static_cast<int32_t*>(take(m * 4));
+  w.creator = static_cast<uint16_t*>(take(m * 2));
+  w.members_raw = static_cast<int32_t*>(take(cap_votes * 4));
+  w.bytes = o;
+  return w;
+}
+
+}  // namespace
+}  // namespace sod
+
+using namespace sod;
+
+extern "C" {
+
+size_t sod_compact_scratch_bytes(int64_t n_query) {
+  const int64_t blocks = n_query <= 0 ? 1 : (n_query + kCompactThreads - 1) / kCompactThreads;
+  return static_cast<size_t>(2 * (blocks + 1)) * 4;
+}
+
+int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t* match_q,
+                        int32_t* match_t, int32_t* n_out, void* scratch, sod_stream_t stream) {
+  SOD_CHECK_ARG(n_query >= 0, "n_query < 0");
+  SOD_CHECK_ARG(n_out, "null n_out");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_query == 0) {
+    SOD_CHECK_CUDA(cudaMemsetAsync(n_out, 0, 4, st));
+    return SOD_OK;
+  }
+  SOD_CHECK_ARG(idx && pass && match_q && match_t && scratch, "null pointer");
+  const int64_t blocks = (n_query + kCompactThreads - 1) / kCompactThreads;
+  int32_t* counts = static_cast<int32_t*>(scratch);
+  int32_t* offs = counts + blocks + 1;
+  compact_count_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(pass, n_query, counts);
+  SOD_CHECK_LAUNCH("compact_count_kernel");
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, blocks, offs, nullptr, n_out);
+  SOD_CHECK_LAUNCH("exclusive_scan_kernel");
+  compact_write_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(
+      idx, pass, n_query, offs, match_q, match_t);
+  SOD_CHECK_LAUNCH("compact_write_kernel");
+  return SOD_OK;
+}
+
+size_t sod_hough_workspace_bytes(int64_t n_matches, int64_t n_groups) {
+  if (n_matches < 0) n_matches = 0;
+  if (n_groups < 1) n_groups = 1;
+  return carve_hough_ws(nullptr, n_matches, n_groups, n_matches * 16).bytes + 256;
+}
+
+int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                   int64_t n_matches, const int32_t* n_matches_dev, int32_t bins,
+                   const int32_t* sigma_lut, const sod_hough_out* out, void* workspace,
+                   size_t workspace_bytes, sod_stream_t stream) {
+  SOD_CHECK_ARG(scene && out, "null scene/out");
+  SOD_CHECK_ARG(n_matches >= 0 && n_matches < (int64_t(1) << 27), "n_matches out of range");
+  SOD_CHECK_ARG(bins >= 1, "bins < 1");
+  if (bins > SOD_MAX_BINS) {
+    set_error("bins = %d: the shared-memory histogram holds at most %d^4 counters", bins, SOD_MAX_BINS);
+    return SOD_ERR_UNSUPPORTED;
+  }
+  SOD_CHECK_ARG(out->counters, "null counters");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SOD_CHECK_CUDA(cudaMemsetAsync(out->counters, 0, 4 * sizeof(int32_t), st));
+  if (n_matches == 0) return SOD_OK;
+  const int64_t n_groups = static_cast<int64_t>(scene->n_frames) * scene->groups_per_frame;
+  SOD_CHECK_ARG(scene->n_frames >= 1 && scene->groups_per_frame >= 1 && n_groups < (int64_t(1) << 30),
+                "bad frame/group counts");
+  SOD_CHECK_ARG(match_q && match_t && sigma_lut && workspace, "null pointer");
+  SOD_CHECK_ARG(scene->query.xy && scene->query.angle && scene->query.octave && scene->model.xy &&
+                    scene->model.angle && scene->model.octave && scene->model_image &&
+                    scene->image_centroid && scene->image_size && scene->frame_wh,
+                "null scene array");
+  SOD_CHECK_ARG(out->pose && out->base_bin && out->near_edge && out->bin_group && out->bin_code &&
+                    out->bin_count && out->bin_offset && out->bin_order && out->bin_mean && out->members,
+                "null output array");
+  SOD_CHECK_ARG(out->cap_votes < (int64_t(1) << 31) && out->cap_bins < (int64_t(1) << 31), "capacity >= 2^31");
+  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  const int64_t raw_cap = out->cap_votes < n_matches * 16 ? out->cap_votes : n_matches * 16;
+  const HoughWs w = carve_hough_ws(workspace, n_matches, n_groups, raw_cap);
+  SOD_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+  const int sms = device_sm_count();
+  if (sms <= 0) return SOD_ERR_CUDA;
+
+  SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_groups + 1) * 4, st));
+  PoseArgs pa;
+  pa.sc = *scene;
+  pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = n_matches_dev; pa.n_cap = n_matches;
+  pa.bins = bins; pa.sigma_lut = sigma_lut; pa.pose = out->pose; pa.base_bin = out->base_bin;
+  pa.near_edge = out->near_edge; pa.counters = out->counters; pa.group_of = w.group_of;
+  pa.group_count = w.group_count;
+  const int threads = 256;
+  int64_t blocks = (n_matches + threads - 1) / threads;
+  if (blocks > static_cast<int64_t>(sms) * 16) blocks = static_cast<int64_t>(sms) * 16;
+  hough_pose_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(pa);
+  SOD_CHECK_LAUNCH("hough_pose_kernel");
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.group_count, n_groups, w.group_off, w.group_cursor, nullptr);
+  SOD_CHECK_LAUNCH("exclusive_scan_kernel");
+  group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(w.group_of, n_matches_dev,
+                                                                          n_matches, w.group_cursor, w.grouped);
+  SOD_CHECK_LAUNCH("group_scatter_kernel");
+
+  VoteArgs va;
+  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = out->base_bin; va.creator = w.creator;
+  va.n_groups = n_groups; va.bins = bins; va.counters = out->counters; va.bin_group = out->bin_group;
+  va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
+  va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
+  const size_t hist_bytes = static_cast<size_t>(bins) * bins * bins * bins * sizeof(uint32_t);
+  static size_t attr_bytes = 0;
+  if (hist_bytes > attr_bytes) {
+    SOD_CHECK_CUDA(cudaFuncSetAttribute(hough_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(hist_bytes)));
+    attr_bytes = hist_bytes;
+  }
+  const int64_t vgrid = n_groups < sms ? n_groups : sms;
+  hough_vote_kernel<<<static_cast<unsigned>(vgrid), kVoteThreads, hist_bytes, st>>>(va);
+  SOD_CHECK_LAUNCH("hough_vote_kernel");
+
+  FinishArgs fa;
+  fa.sc = *scene;
+  fa.match_t = match_t; fa.pose = out->pose; fa.base_bin = out->base_bin; fa.counters = out->counters;
+  fa.bin_code = out->bin_code; fa.bin_count = out->bin_count; fa.bin_offset = out->bin_offset;
+  fa.members_raw = w.members_raw; fa.members = out->members; fa.bin_order = out->bin_order;
+  fa.bin_mean = out->bin_mean; fa.cap_bins = out->cap_bins; fa.bins = bins;
+  hough_finish_kernel<<<sms * 8, 256, 0, st>>>(fa);
+  SOD_CHECK_LAUNCH("hough_finish_kernel");
+  return SOD_OK;
+}
+
+}  // extern "C"

@@ -34,6 +34,33 @@ _p = C.c_void_p
 _i64 = C.c_int64
 _i32 = C.c_int32
 
+
+
+class Keypoints(C.Structure):
+    _fields_ = [("xy", _p), ("angle", _p), ("octave", _p), ("n", _i64)]
+
+
+class Scene(C.Structure):
+    _fields_ = [("query", Keypoints), ("query_frame", _p), ("frame_wh", _p), ("n_frames", _i32),
+                ("model", Keypoints), ("model_image", _p), ("image_centroid", _p), ("image_size", _p),
+                ("image_group", _p), ("n_images", _i32), ("groups_per_frame", _i32)]
+
+
+class HoughOut(C.Structure):
+    _fields_ = [("pose", _p), ("base_bin", _p), ("near_edge", _p), ("counters", _p), ("bin_group", _p),
+                ("bin_code", _p), ("bin_count", _p), ("bin_offset", _p), ("bin_order", _p),
+                ("bin_mean", _p), ("members", _p), ("cap_bins", _i64), ("cap_votes", _i64)]
+
+
+class AffineOut(C.Structure):
+    _fields_ = [("counters", _p), ("valid_bin", _p), ("params", _p), ("votes", _p), ("status", _p),
+                ("member_keep", _p), ("cap_valid", _i64)]
+
+
+SIGMA_LUT_MIN = -24
+SIGMA_LUT_LEN = 49
+MAX_BINS = 15
+
 _PROTOS = {
     "sod_version": (C.c_int, []),
     "sod_last_error": (C.c_char_p, []),
@@ -45,6 +72,13 @@ _PROTOS = {
     "sod_match_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "sod_match_top2": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p, C.c_size_t, _p]),
     "sod_top2_merge": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, _p, C.c_double, _p]),
+    "sod_compact_scratch_bytes": (C.c_size_t, [_i64]),
+    "sod_compact_matches": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p]),
+    "sod_hough_workspace_bytes": (C.c_size_t, [_i64, _i64]),
+    "sod_hough_vote": (C.c_int, [C.POINTER(Scene), _p, _p, _i64, _p, _i32, _p, C.POINTER(HoughOut), _p,
+                                 C.c_size_t, _p]),
+    "sod_affine_verify": (C.c_int, [C.POINTER(Scene), _p, _p, C.POINTER(HoughOut), _i32, _i32, _i32,
+                                    C.c_double, C.POINTER(AffineOut), _p]),
 }
 
 

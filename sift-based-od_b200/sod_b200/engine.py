@@ -129,3 +129,194 @@ def knn_match_ratio(q_u8: torch.Tensor, matcher: Matcher, ratio: float = RATIO):
     """Single-shard convenience: knnMatch(k=2) + ratio flags."""
     idx, d2 = matcher.top2(q_u8)
     return merge_top2(idx[None], d2[None], ratio)
+
+
+# ------------------------------------------------------------------------------------------------
+# Hough voting + affine verification
+# ------------------------------------------------------------------------------------------------
+import math  # noqa: E402
+
+from ._capi import AffineOut, HoughOut, Keypoints, Scene  # noqa: E402
+
+POS_FACTOR = 32          # main.py:141
+N_OCT = 4                # HoughTransformHelperFunctions.py:66
+
+
+def sigma_lut(bins: int) -> list[int]:
+    """isigma of scale factor 2^k for k = -24..24, evaluated with the host libm exactly as
+    HoughTransformHelperFunctions.py:66-70 does; the scale ratio of two SIFT octaves is always 2^k."""
+    out = []
+    for k in range(_capi.SIGMA_LUT_MIN, _capi.SIGMA_LUT_MIN + _capi.SIGMA_LUT_LEN):
+        i = int(math.log(2.0 ** k, 2) / (2 * (N_OCT - 1) + 0.5) * bins)
+        out.append(min(max(0, i), bins - 1))
+    return out
+
+
+def _dev(x, dtype, device):
+    t = torch.as_tensor(x)
+    return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+class SceneArrays:
+    """Device-resident structure-of-arrays for the Hough/affine stages (sod_scene in sod.h)."""
+
+    def __init__(self, q_xy, q_angle, q_octave, m_xy, m_angle, m_octave, m_image, img_centroid, img_size,
+                 frame_wh, q_frame=None, img_group=None, groups_per_frame: int = 1, device="cuda"):
+        d = torch.device(device)
+        self.q_xy = _dev(q_xy, torch.float32, d).reshape(-1, 2)
+        self.q_angle = _dev(q_angle, torch.float32, d)
+        self.q_octave = _dev(q_octave, torch.int32, d)
+        self.m_xy = _dev(m_xy, torch.float32, d).reshape(-1, 2)
+        self.m_angle = _dev(m_angle, torch.float32, d)
+        self.m_octave = _dev(m_octave, torch.int32, d)
+        self.m_image = _dev(m_image, torch.int32, d)
+        self.img_centroid = _dev(img_centroid, torch.float64, d).reshape(-1, 2)
+        self.img_size = _dev(img_size, torch.float64, d).reshape(-1, 2)
+        self.frame_wh = _dev(frame_wh, torch.int32, d).reshape(-1, 2)
+        self.q_frame = None if q_frame is None else _dev(q_frame, torch.int32, d)
+        self.img_group = None if img_group is None else _dev(img_group, torch.int32, d)
+        self.groups_per_frame = int(groups_per_frame)
+        self.device = d
+        n_img = self.img_centroid.shape[0]
+        if self.img_size.shape[0] != n_img or self.m_image.numel() != self.m_xy.shape[0]:
+            raise ValueError("inconsistent model arrays")
+
+    @property
+    def n_frames(self) -> int:
+        return int(self.frame_wh.shape[0])
+
+    @property
+    def n_groups(self) -> int:
+        return self.n_frames * self.groups_per_frame
+
+    def struct(self) -> Scene:
+        return Scene(
+            Keypoints(_ptr(self.q_xy), _ptr(self.q_angle), _ptr(self.q_octave), self.q_xy.shape[0]),
+            _ptr(self.q_frame), _ptr(self.frame_wh), self.n_frames,
+            Keypoints(_ptr(self.m_xy), _ptr(self.m_angle), _ptr(self.m_octave), self.m_xy.shape[0]),
+            _ptr(self.m_image), _ptr(self.img_centroid), _ptr(self.img_size), _ptr(self.img_group),
+            int(self.img_centroid.shape[0]), self.groups_per_frame)
+
+
+def compact_matches(idx: torch.Tensor, ok: torch.Tensor):
+    """Ratio survivors in query order -> (match_q, match_t, n_dev); stays on the device."""
+    idx = _require_cuda(idx, torch.int32, "idx")
+    ok = _require_cuda(ok, torch.uint8, "pass flags")
+    nq = int(ok.shape[0])
+    dev = idx.device
+    mq = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+    mt = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(lib.sod_compact_scratch_bytes(nq)), dtype=torch.uint8, device=dev)
+    check(lib.sod_compact_matches(_ptr(idx), _ptr(ok), nq, _ptr(mq), _ptr(mt), _ptr(n), _ptr(scratch),
+                                  _stream()), "sod_compact_matches")
+    return mq, mt, n
+
+
+class HoughResult:
+    """Device outputs of sod_hough_vote plus the host view used to build PoseBin objects."""
+
+    def __init__(self, m_cap: int, n_groups: int, bins: int, device):
+        self.bins = bins
+        self.m_cap = m_cap
+        nb4 = bins ** 4
+        self.cap_bins = max(1, min(16 * m_cap, n_groups * nb4))
+        self.cap_votes = max(1, 16 * m_cap)
+        e = lambda n, dt: torch.empty(n, dtype=dt, device=device)  # noqa: E731
+        self.pose = e((max(m_cap, 1), 4), torch.float64)
+        self.base_bin = e(max(m_cap, 1), torch.int32)
+        self.near_edge = e(max(m_cap, 1), torch.uint8)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=device)
+        self.bin_group = e(self.cap_bins, torch.int32)
+        self.bin_code = e(self.cap_bins, torch.int32)
+        self.bin_count = e(self.cap_bins, torch.int32)
+        self.bin_offset = e(self.cap_bins, torch.int32)
+        self.bin_order = e(self.cap_bins, torch.int64)
+        self.bin_mean = e((self.cap_bins, 6), torch.float64)
+        self.members = e(self.cap_votes, torch.int32)
+
+    def struct(self) -> HoughOut:
+        return HoughOut(_ptr(self.pose), _ptr(self.base_bin), _ptr(self.near_edge), _ptr(self.counters),
+                        _ptr(self.bin_group), _ptr(self.bin_code), _ptr(self.bin_count),
+                        _ptr(self.bin_offset), _ptr(self.bin_order), _ptr(self.bin_mean),
+                        _ptr(self.members), self.cap_bins, self.cap_votes)
+
+    def host(self) -> dict:
+        """Synchronise and return numpy arrays with the bins in reference insertion order."""
+        c = self.counters.cpu().numpy()
+        if c[3]:
+            raise _capi.SodError("Hough output capacity exceeded")
+        nb, nv = int(c[0]), int(c[1])
+        order = torch.argsort(self.bin_order[:nb])
+        g = lambda t: t[:nb][order].cpu().numpy()  # noqa: E731
+        return dict(n_bins=nb, n_votes=nv, n_near_edge=int(c[2]), rec=order.cpu().numpy(),
+                    group=g(self.bin_group), code=g(self.bin_code), count=g(self.bin_count),
+                    offset=g(self.bin_offset), mean=g(self.bin_mean), order_key=g(self.bin_order),
+                    members=self.members[:nv].cpu().numpy())
+
+
+class HoughVoter:
+    """Caches workspace / outputs across calls of the same capacity."""
+
+    def __init__(self, scene: SceneArrays, bins: int = 15):
+        if bins > _capi.MAX_BINS:
+            raise _capi.SodError(f"bins={bins} > {_capi.MAX_BINS}: not supported by the shared-memory histogram")
+        self.scene = scene
+        self.bins = int(bins)
+        self.lut = torch.tensor(sigma_lut(self.bins), dtype=torch.int32, device=scene.device)
+        self._ws = None
+        self._res: HoughResult | None = None
+
+    def vote(self, match_q: torch.Tensor, match_t: torch.Tensor, n_dev: torch.Tensor | None = None) -> HoughResult:
+        match_q = _require_cuda(match_q, torch.int32, "match_q")
+        match_t = _require_cuda(match_t, torch.int32, "match_t")
+        m = int(match_q.shape[0])
+        sc = self.scene
+        need = int(lib.sod_hough_workspace_bytes(m, sc.n_groups))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=sc.device)
+        if self._res is None or self._res.m_cap < m:
+            self._res = HoughResult(m, sc.n_groups, self.bins, sc.device)
+        res = self._res
+        s, o = sc.struct(), res.struct()
+        check(lib.sod_hough_vote(C.byref(s), _ptr(match_q), _ptr(match_t), m, _ptr(n_dev), self.bins,
+                                 _ptr(self.lut), C.byref(o), _ptr(self._ws), self._ws.numel(), _stream()),
+              "sod_hough_vote")
+        return res
+
+
+class AffineResult:
+    def __init__(self, hough: HoughResult, vote_threshold: int, device):
+        self.cap_valid = max(1, min(hough.cap_bins, hough.cap_votes // max(vote_threshold, 1)))
+        self.counters = torch.zeros(2, dtype=torch.int32, device=device)
+        self.valid_bin = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
+        self.params = torch.empty((self.cap_valid, 6), dtype=torch.float64, device=device)
+        self.votes = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
+        self.status = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
+        self.member_keep = torch.empty(hough.cap_votes, dtype=torch.uint8, device=device)
+
+    def struct(self) -> AffineOut:
+        return AffineOut(_ptr(self.counters), _ptr(self.valid_bin), _ptr(self.params), _ptr(self.votes),
+                         _ptr(self.status), _ptr(self.member_keep), self.cap_valid)
+
+    def host(self, n_votes: int) -> dict:
+        c = self.counters.cpu().numpy()
+        if c[1]:
+            raise _capi.SodError("affine output capacity exceeded")
+        nv = int(c[0])
+        st = self.status[:nv].cpu().numpy()
+        return dict(n_valid=nv, valid_bin=self.valid_bin[:nv].cpu().numpy(),
+                    params=self.params[:nv].cpu().numpy(), votes=self.votes[:nv].cpu().numpy(),
+                    live=(st & 1).astype(bool), singular=((st >> 1) & 1).astype(bool), passes=st >> 8,
+                    member_keep=self.member_keep[:n_votes].cpu().numpy().astype(bool))
+
+
+def affine_verify(scene: SceneArrays, match_q: torch.Tensor, match_t: torch.Tensor, hough: HoughResult,
+                  vote_threshold: int = 5, affine_threshold: int = 4, factor: float = POS_FACTOR * 4,
+                  result: AffineResult | None = None) -> AffineResult:
+    res = result or AffineResult(hough, vote_threshold, scene.device)
+    s, h, o = scene.struct(), hough.struct(), res.struct()
+    check(lib.sod_affine_verify(C.byref(s), _ptr(match_q), _ptr(match_t), C.byref(h), hough.bins,
+                                int(vote_threshold), int(affine_threshold), float(factor), C.byref(o),
+                                _stream()), "sod_affine_verify")
+    return res
