@@ -143,6 +143,18 @@ size_t sod_compact_scratch_bytes(int64_t n_query);
 int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t* match_q,
                         int32_t* match_t, int32_t* n_out, void* scratch, sod_stream_t stream);
 
+/* estimate_object_pose + calculate_bin_index only (HoughTransformHelperFunctions.py:4-72), no voting:
+ * pose [n][4] and base_bin [n] as in sod_hough_out; near_edge may be NULL. */
+int sod_estimate_pose(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                      int64_t n_matches, int32_t bins, const int32_t* sigma_lut, double* pose,
+                      uint32_t* base_bin, uint8_t* near_edge, sod_stream_t stream);
+
+/* calculate_bin_index (HoughTransformHelperFunctions.py:39-72) for caller-supplied poses
+ * (x, y, theta, scale) [n][4] -> packed base bins.  Scales that are not powers of two take
+ * log(s)/log(2) on the device (last-bit differences from the host libm are possible there). */
+int sod_pose_bin_index(const double* pose, int64_t n, int32_t bins, int32_t width, int32_t height,
+                       const int32_t* sigma_lut, uint32_t* base_bin, sod_stream_t stream);
+
 /* Bytes of scratch for sod_hough_vote. */
 size_t sod_hough_workspace_bytes(int64_t n_matches, int64_t n_groups);
 
@@ -172,12 +184,20 @@ typedef struct {
 /* K5.  Main.get_valid_bins + Main.apply_affine_parameters (main.py:121-157) with AffineParameters
  * and remove_outliers (AffineParameters.py:89-160): per bin, fit u = m1 x + m2 y + tx,
  * v = m3 x + m4 y + ty by the pseudo-inverse of the normal matrix (rcond 1e-15), drop pairs whose
- * residual exceeds W*isigma/factor or H*isigma/factor, repeat until nothing is dropped or fewer than
- * affine_threshold pairs remain. */
+ * residual exceeds W*isigma/factor_x or H*isigma/factor_y, repeat until nothing is dropped or fewer
+ * than affine_threshold pairs remain.  max_passes > 0 stops after that many fit/prune passes
+ * (1 = one AffineParameters + remove_outliers call); factor <= 0 disables pruning on that axis
+ * (a pure fit). */
 int sod_affine_verify(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
                       const sod_hough_out* hough, int32_t bins, int32_t vote_threshold,
-                      int32_t affine_threshold, double factor, const sod_affine_out* out,
-                      sod_stream_t stream);
+                      int32_t affine_threshold, double factor_x, double factor_y, int32_t max_passes,
+                      const sod_affine_out* out, sod_stream_t stream);
+
+/* remove_outliers' decision for caller-supplied parameters (AffineParameters.py:128-155):
+ * keep[i] = !(|m1 x + m2 y + tx - u| > x_ref || |m3 x + m4 y + ty - v| > y_ref), params on the device. */
+int sod_affine_residual_keep(const float* model_xy, const float* query_xy, int64_t n,
+                             const double* params, double x_ref, double y_ref, uint8_t* keep,
+                             sod_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,8 +27,8 @@ struct AffineArgs {
   const int32_t* bin_offset;
   const int32_t* members;
   int64_t cap_bins;
-  int bins, vote_threshold, affine_threshold;
-  double factor;
+  int bins, vote_threshold, affine_threshold, max_passes;
+  double factor_x, factor_y;
   sod_affine_out out;
 };
 
@@ -101,8 +101,9 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
     const int frame = a.bin_group[rec] / a.sc.groups_per_frame;
     const int isigma = a.bin_code[rec] % a.bins;
     // remove_outliers thresholds use pose[3], the sigma BIN INDEX (AffineParameters.py:120-121)
-    const double x_ref = __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame] * isigma), a.factor);
-    const double y_ref = __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double x_ref = a.factor_x > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame] * isigma), a.factor_x) : inf;
+    const double y_ref = a.factor_y > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor_y) : inf;
     uint8_t* keep = a.out.member_keep + off;
     const int32_t* mem = a.members + off;
     for (int j = lane; j < cnt; j += 32) keep[j] = 1;
@@ -166,6 +167,7 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
       ++passes;
       if (alive < a.affine_threshold) break;  // dropped from valid_bins after this pass
       if (removed == 0) { live = 1; break; }
+      if (a.max_passes > 0 && passes >= a.max_passes) { live = 1; break; }
     }
     if (lane == 0) {
       double* p = a.out.params + v * 6;
@@ -176,21 +178,47 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
   }
 }
 
+// remove_outliers with caller-supplied parameters (AffineParameters.py:128-155).
+__global__ void affine_residual_kernel(const float2* __restrict__ mxy, const float2* __restrict__ qxy,
+                                       int64_t n, const double* __restrict__ p, double x_ref,
+                                       double y_ref, uint8_t* __restrict__ keep) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = mxy[i].x, y = mxy[i].y;
+  const double ua = __dadd_rn(__dadd_rn(__dmul_rn(p[0], x), __dmul_rn(p[1], y)), p[4]);
+  const double va = __dadd_rn(__dadd_rn(__dmul_rn(p[2], x), __dmul_rn(p[3], y)), p[5]);
+  keep[i] = !(fabs(ua - static_cast<double>(qxy[i].x)) > x_ref || fabs(va - static_cast<double>(qxy[i].y)) > y_ref);
+}
+
 }  // namespace
 }  // namespace sod
 
 using namespace sod;
 
+extern "C" int sod_affine_residual_keep(const float* model_xy, const float* query_xy, int64_t n,
+                                        const double* params, double x_ref, double y_ref,
+                                        uint8_t* keep, sod_stream_t stream) {
+  SOD_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return SOD_OK;
+  SOD_CHECK_ARG(model_xy && query_xy && params && keep, "null pointer");
+  const int threads = 256;
+  affine_residual_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0,
+                           static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(model_xy), reinterpret_cast<const float2*>(query_xy), n, params,
+      x_ref, y_ref, keep);
+  SOD_CHECK_LAUNCH("affine_residual_kernel");
+  return SOD_OK;
+}
+
 extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
                                  const sod_hough_out* hough, int32_t bins, int32_t vote_threshold,
-                                 int32_t affine_threshold, double factor, const sod_affine_out* out,
-                                 sod_stream_t stream) {
+                                 int32_t affine_threshold, double factor_x, double factor_y,
+                                 int32_t max_passes, const sod_affine_out* out, sod_stream_t stream) {
   SOD_CHECK_ARG(scene && hough && out, "null scene/hough/out");
   SOD_CHECK_ARG(out->counters && out->valid_bin && out->params && out->votes && out->status &&
                     out->member_keep && out->cap_valid > 0,
                 "null output array");
-  SOD_CHECK_ARG(bins >= 1 && bins <= SOD_MAX_BINS, "bins out of range");
-  SOD_CHECK_ARG(factor > 0, "factor must be positive");
+  SOD_CHECK_ARG(bins >= 1, "bins out of range");
   SOD_CHECK_ARG(match_q && match_t && hough->counters && hough->bin_group && hough->bin_code &&
                     hough->bin_count && hough->bin_offset && hough->members,
                 "null input array");
@@ -204,7 +232,7 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
   a.bin_group = hough->bin_group; a.bin_code = hough->bin_code; a.bin_count = hough->bin_count;
   a.bin_offset = hough->bin_offset; a.members = hough->members; a.cap_bins = hough->cap_bins;
   a.bins = bins; a.vote_threshold = vote_threshold; a.affine_threshold = affine_threshold;
-  a.factor = factor; a.out = *out;
+  a.factor_x = factor_x; a.factor_y = factor_y; a.max_passes = max_passes; a.out = *out;
   affine_select_kernel<<<sms * 4, 256, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_select_kernel");
   affine_verify_kernel<<<sms * 8, 128, 0, st>>>(a);

@@ -106,11 +106,43 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
     a.base_bin[i] = static_cast<uint32_t>(ix) | (static_cast<uint32_t>(iy) << 8) |
                     (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
     const bool edge = near_integer(fx) || near_integer(fy) || near_integer(ft);
-    a.near_edge[i] = edge ? 1 : 0;
-    if (edge) atomicAdd(&a.counters[2], 1);
-    a.group_of[i] = grp;
-    atomicAdd(&a.group_count[grp], 1);
+    if (a.near_edge) a.near_edge[i] = edge ? 1 : 0;
+    if (edge && a.counters) atomicAdd(&a.counters[2], 1);
+    if (a.group_of) {
+      a.group_of[i] = grp;
+      atomicAdd(&a.group_count[grp], 1);
+    }
   }
+}
+
+// calculate_bin_index for caller-supplied poses (the drop-in helper of the same name).  The scale
+// need not be a power of two here: exact powers use the table, others log(s)/log(2) on the device.
+__global__ void pose_bin_index_kernel(const double* __restrict__ pose, int64_t n, int bins, double W,
+                                      double H, const int32_t* __restrict__ sigma_lut,
+                                      uint32_t* __restrict__ base_bin) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pose[4 * i], y = pose[4 * i + 1], al = pose[4 * i + 2], s = pose[4 * i + 3];
+  const double fx = __ddiv_rn(__dmul_rn(x, static_cast<double>(bins)), W);
+  const double fy = __ddiv_rn(__dmul_rn(y, static_cast<double>(bins)), H);
+  double ft = fmod(__ddiv_rn(__dmul_rn(al, static_cast<double>(bins)), kTwoPi), static_cast<double>(bins));
+  if (ft < 0.0) ft = __dadd_rn(ft, static_cast<double>(bins));  // Python's % follows the divisor's sign
+  int ix = static_cast<int>(fmin(fmax(trunc(fx), -1.0e6), 1.0e6));
+  int iy = static_cast<int>(fmin(fmax(trunc(fy), -1.0e6), 1.0e6));
+  ix = min(max(0, ix - 1), bins - 1);
+  iy = min(max(0, iy - 1), bins - 1);
+  int it = min(max(static_cast<int>(ft), 0), bins - 1);
+  int e = 0;
+  const double mant = frexp(s, &e);
+  int is;
+  if (mant == 0.5 && e - 1 >= SOD_SIGMA_LUT_MIN && e - 1 < SOD_SIGMA_LUT_MIN + SOD_SIGMA_LUT_LEN) {
+    is = sigma_lut[e - 1 - SOD_SIGMA_LUT_MIN];
+  } else {
+    const double v = __dmul_rn(__ddiv_rn(__ddiv_rn(log(s), log(2.0)), 6.5), static_cast<double>(bins));
+    is = min(max(static_cast<int>(fmin(fmax(trunc(v), -1.0e6), 1.0e6)), 0), bins - 1);
+  }
+  base_bin[i] = static_cast<uint32_t>(ix) | (static_cast<uint32_t>(iy) << 8) |
+                (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
 }
 
 // Exclusive scan of n ints by one CTA (n is the number of Hough spaces: small).
@@ -453,6 +485,42 @@ int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query
   compact_write_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(
       idx, pass, n_query, offs, match_q, match_t);
   SOD_CHECK_LAUNCH("compact_write_kernel");
+  return SOD_OK;
+}
+
+int sod_estimate_pose(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                      int64_t n_matches, int32_t bins, const int32_t* sigma_lut, double* pose,
+                      uint32_t* base_bin, uint8_t* near_edge, sod_stream_t stream) {
+  SOD_CHECK_ARG(scene && n_matches >= 0, "bad arguments");
+  if (n_matches == 0) return SOD_OK;
+  SOD_CHECK_ARG(bins >= 1 && bins <= 255, "bins out of range");
+  SOD_CHECK_ARG(match_q && match_t && sigma_lut && pose && base_bin, "null pointer");
+  SOD_CHECK_ARG(scene->query.xy && scene->query.angle && scene->query.octave && scene->model.xy &&
+                    scene->model.angle && scene->model.octave && scene->model_image &&
+                    scene->image_centroid && scene->frame_wh && scene->groups_per_frame >= 1,
+                "null scene array");
+  PoseArgs pa;
+  pa.sc = *scene;
+  pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = nullptr; pa.n_cap = n_matches;
+  pa.bins = bins; pa.sigma_lut = sigma_lut; pa.pose = pose; pa.base_bin = base_bin;
+  pa.near_edge = near_edge; pa.counters = nullptr; pa.group_of = nullptr; pa.group_count = nullptr;
+  const int threads = 256;
+  hough_pose_kernel<<<static_cast<unsigned>((n_matches + threads - 1) / threads), threads, 0,
+                      static_cast<cudaStream_t>(stream)>>>(pa);
+  SOD_CHECK_LAUNCH("hough_pose_kernel");
+  return SOD_OK;
+}
+
+int sod_pose_bin_index(const double* pose, int64_t n, int32_t bins, int32_t width, int32_t height,
+                       const int32_t* sigma_lut, uint32_t* base_bin, sod_stream_t stream) {
+  SOD_CHECK_ARG(n >= 0 && bins >= 1 && bins <= 255 && width > 0 && height > 0, "bad arguments");
+  if (n == 0) return SOD_OK;
+  SOD_CHECK_ARG(pose && sigma_lut && base_bin, "null pointer");
+  const int threads = 256;
+  pose_bin_index_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0,
+                          static_cast<cudaStream_t>(stream)>>>(pose, n, bins, width, height, sigma_lut,
+                                                               base_bin);
+  SOD_CHECK_LAUNCH("pose_bin_index_kernel");
   return SOD_OK;
 }
 

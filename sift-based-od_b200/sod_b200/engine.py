@@ -313,10 +313,12 @@ class AffineResult:
 
 def affine_verify(scene: SceneArrays, match_q: torch.Tensor, match_t: torch.Tensor, hough: HoughResult,
                   vote_threshold: int = 5, affine_threshold: int = 4, factor: float = POS_FACTOR * 4,
-                  result: AffineResult | None = None) -> AffineResult:
+                  result: AffineResult | None = None, factor_y: float | None = None,
+                  max_passes: int = 0) -> AffineResult:
     res = result or AffineResult(hough, vote_threshold, scene.device)
     s, h, o = scene.struct(), hough.struct(), res.struct()
     check(lib.sod_affine_verify(C.byref(s), _ptr(match_q), _ptr(match_t), C.byref(h), hough.bins,
-                                int(vote_threshold), int(affine_threshold), float(factor), C.byref(o),
-                                _stream()), "sod_affine_verify")
+                                int(vote_threshold), int(affine_threshold), float(factor),
+                                float(factor if factor_y is None else factor_y), int(max_passes),
+                                C.byref(o), _stream()), "sod_affine_verify")
     return res
