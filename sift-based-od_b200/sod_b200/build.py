@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-lcudart_static", "-ldl", "-lrt",
+              "-lpthread"]
+
+
 def _nvcc() -> str:
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
@@ -43,7 +47,7 @@ def _digest() -> str:
                     [PKG_DIR.parent.parent / "include" / "sod.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + LINK_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -68,8 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart_static", "-ldl", "-lrt",
-           "-lpthread"]
+    cmd = [nvcc, "-o", str(LIB_PATH), *map(str, objs), *LINK_FLAGS]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

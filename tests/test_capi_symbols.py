@@ -1,0 +1,55 @@
+"""CPU-side checks of the boundary: the library builds, loads without a GPU, exports exactly the
+functions include/sod.h declares, and argument errors are reported through status codes."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _header_functions():
+    text = (ROOT / "include" / "sod.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sod_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sod_b200 import _capi
+    declared = _header_functions()
+    assert len(declared) >= 15
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_capi._LIB_PATH)], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (sod_[a-z0-9_]+)", out)))
+    assert exported == declared
+    assert sorted(_capi.EXPORTED) == declared          # the ctypes binding covers all of them
+
+
+def test_library_has_blackwell_code_only():
+    from sod_b200 import _capi
+    out = subprocess.run(["cuobjdump", "-lelf", str(_capi._LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_error_reporting_without_gpu():
+    from sod_b200 import _capi
+    lib = _capi.lib
+    assert lib.sod_version() >= 1000
+    assert lib.sod_cq_ints(0) == 0 and lib.sod_cq_ints(1) == 132 and lib.sod_cq_ints(129) == 264
+    rc = lib.sod_db_prepare(None, -1, None, None)
+    assert rc == -1 and b"n_rows" in lib.sod_last_error()
+    rc = lib.sod_top2_merge(None, None, 1, 10, None, None, None, None, 0.75, None)
+    assert rc == -1 and b"null" in lib.sod_last_error()
+    assert lib.sod_compact_scratch_bytes(5000) >= 8 * 6
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = ROOT / "sift-based-od_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        text = f.read_text()
+        assert "oracle" not in text.lower() or f.name == "build.py", f"{f} mentions the oracle"
+
+
+def test_graft_entry_build():
+    import __graft_entry__ as g
+    g.build()
