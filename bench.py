@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Headline benchmark: query descriptors/s through kNN2 + ratio + Hough + affine against a
+1M-descriptor model database (BASELINE.json), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, rank 0 only
+
+Workload (BASELINE.json configs[3], "throughput mode"): 256 scene frames x 5,000 SIFT descriptors
+against 1,000 model objects x 1,000 descriptors, u8 128-d, synthetic (seeded).  Every frame contains
+4 planted object instances (10 % of its descriptors are true matches) plus 1 % descriptor-only false
+matches; Hough spaces are per (frame, object).  A step is one pass of the whole path over the batch.
+N > 1: database rows sharded object-aligned across ranks, queries replicated, one all-gather of the
+shard-local top-2 (16 B/query), Hough + affine for each rank's own objects => fixed total work,
+"scaling": "strong".
+
+Timed regions
+  value : inputs resident in HBM; CUDA events on the launching stream, barrier + synchronize on both
+          sides, max over ranks.
+  e2e   : the public API (sod_b200.pipeline.DetectionPipeline.detect) with pinned HOST buffers:
+          H2D of descriptors + keypoints and D2H of matches + verified bins inside the region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+sys.path.insert(0, str(ROOT))
+
+METRIC = "query descriptors/sec (kNN2+ratio+Hough+affine), 1M-desc DB"
+UNIT = "query descriptors/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+def sift_like_torch(n, gen, device):
+    import torch
+    x = torch.randn((n, 128), device=device, generator=gen).abs_()
+    x /= x.norm(dim=1, keepdim=True)
+    x.clamp_(max=0.2)
+    x /= x.norm(dim=1, keepdim=True)
+    return (x * 512).round_().clamp_(0, 255).to(torch.uint8)
+
+
+def make_workload(args, device):
+    """Deterministic (seed 102) on every rank.  Descriptors are generated with torch on `device`
+    (fast for 1M x 128); geometry with numpy."""
+    import torch
+    n_obj, kpo, frames, per = args.objects, args.kp_per_object, args.frames, args.per_frame
+    ndb, nq = n_obj * kpo, frames * per
+    rng = np.random.default_rng(102)
+    mw, mh, W, H = 1500, 1000, 4032, 3024
+    m_xy = np.stack([rng.uniform(0, mw, ndb), rng.uniform(0, mh, ndb)], 1).astype(np.float32)
+    m_angle = rng.uniform(0, 360, ndb).astype(np.float32)
+    m_oct = rng.integers(0, 3, ndb)
+    m_image = np.repeat(np.arange(n_obj, dtype=np.int32), kpo)
+    cent = m_xy.astype(np.float64).reshape(n_obj, kpo, 2).mean(1)
+    q_xy = np.stack([rng.uniform(0, W, nq), rng.uniform(0, H, nq)], 1).astype(np.float32)
+    q_angle = rng.uniform(0, 360, nq).astype(np.float32)
+    q_oct = rng.integers(-1, 5, nq)
+    q_frame = np.repeat(np.arange(frames, dtype=np.int32), per)
+    inst, n_in = args.instances, int(per * args.inlier_frac) // args.instances
+    src_q, src_t = [], []
+    for f in range(frames):
+        rows = f * per + rng.choice(per, inst * n_in + int(per * args.false_frac), replace=False)
+        objs = rng.choice(n_obj, inst, replace=False)
+        for j, o in enumerate(objs):
+            qi = rows[j * n_in:(j + 1) * n_in]
+            t = o * kpo + rng.choice(kpo, n_in, replace=False)
+            k = int(rng.integers(0, 3))
+            s, th = 2.0 ** k, rng.uniform(0, 2 * math.pi)
+            c = np.array([rng.uniform(0.25, 0.75) * W, rng.uniform(0.25, 0.75) * H])
+            rel = (m_xy[t].astype(np.float64) - cent[o]) * s
+            rot = np.stack([math.cos(th) * rel[:, 0] - math.sin(th) * rel[:, 1],
+                            math.sin(th) * rel[:, 0] + math.cos(th) * rel[:, 1]], 1)
+            q_xy[qi] = (rot + c + rng.normal(0, 2.0, rot.shape)).astype(np.float32)
+            a = np.mod(m_angle[t].astype(np.float64) + math.degrees(th), 360.0).astype(np.float32)
+            q_angle[qi] = np.where(a >= 360.0, 0.0, a)
+            q_oct[qi] = m_oct[t] + k
+            src_q.append(qi)
+            src_t.append(t)
+        fq = rows[inst * n_in:]
+        src_q.append(fq)
+        src_t.append(rng.integers(0, ndb, len(fq)))
+    src_q = np.concatenate(src_q)
+    src_t = np.concatenate(src_t)
+    gen = torch.Generator(device=device).manual_seed(102)
+    db_des = sift_like_torch(ndb, gen, device)
+    q_des = sift_like_torch(nq, gen, device)
+    noise = torch.randint(-3, 4, (len(src_q), 128), device=device, generator=gen, dtype=torch.int16)
+    sq = torch.from_numpy(src_q).to(device)
+    st = torch.from_numpy(src_t).to(device)
+    q_des[sq] = (db_des[st].to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+    pack = lambda o: ((o.astype(np.int64) & 0xFF) | (1 << 8)).astype(np.int32)  # noqa: E731
+    return dict(db_des=db_des, m_xy=m_xy, m_angle=m_angle, m_octave=pack(m_oct), m_image=m_image,
+                img_centroid=cent, img_size=np.tile(np.array([[mw, mh]], np.int32), (n_obj, 1)),
+                q_des=q_des, q_xy=q_xy, q_angle=q_angle, q_octave=pack(q_oct), q_frame=q_frame,
+                frame_wh=np.tile(np.array([[W, H]], np.int32), (frames, 1)), n_true=len(src_q))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path of the reference (cv2.BFMatcher + the Python Hough / affine loops, restated in oracle/)
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, wl, args):
+        import cv2
+        from oracle import sod_oracle as O
+        self.cv2, self.O = cv2, O
+        cv2.setNumThreads(os.cpu_count() or 1)
+        self.threads = cv2.getNumThreads()
+        db = wl["db_des"].cpu().numpy()
+        self.db_f32 = db.astype(np.float32)
+        self.chunk = (1 << 18) - 1  # cv2 asserts on >= 2^18 train rows
+        self.chunks = [self.db_f32[s:s + self.chunk] for s in range(0, len(db), self.chunk)]
+        self.offsets = np.arange(0, len(db), self.chunk)
+        self.wl, self.args = wl, args
+        self.q_des = wl["q_des"].cpu().numpy()
+        self.scene = O.Scene(wl["q_xy"], wl["q_angle"], wl["q_octave"], wl["m_xy"], wl["m_angle"], wl["m_octave"],
+                             wl["m_image"], wl["img_centroid"], wl["img_size"], int(wl["frame_wh"][0, 0]),
+                             int(wl["frame_wh"][0, 1]), np.arange(args.objects, dtype=np.int32))
+
+    def run(self, q_rows: np.ndarray) -> dict:
+        """main.py:180-185 on the given query rows (all from one frame)."""
+        cv2, O = self.cv2, self.O
+        t0 = time.perf_counter()
+        q = self.q_des[q_rows].astype(np.float32)
+        bf = cv2.BFMatcher()
+        bf.add(self.chunks)
+        matches = bf.knnMatch(q, k=2)                                   # main.py:70-71
+        mq, mt = [], []
+        for m, n in matches:                                            # main.py:81-86
+            if m.distance < 0.75 * n.distance:
+                mq.append(int(q_rows[m.queryIdx]))
+                mt.append(int(self.offsets[m.imgIdx] + m.trainIdx))
+        t1 = time.perf_counter()
+        table = O.hough_vote(self.scene, mq, mt, 15)                    # main.py:89-119
+        vb = O.valid_bins(table, 5)                                     # main.py:121-132
+        live = O.affine_verify(self.scene, mq, mt, vb, 4)               # main.py:139-157
+        t2 = time.perf_counter()
+        return dict(n=len(q_rows), t_match=t1 - t0, t_hough_affine=t2 - t1, matches=len(mq), live=len(live))
+
+    def sample_rows(self, step: int, n: int) -> np.ndarray:
+        per = self.args.per_frame
+        f = step % self.args.frames
+        return np.arange(f * per, f * per + min(n, per))
+
+    def calibrate(self, target_s: float) -> int:
+        r = self.run(self.sample_rows(0, 16))
+        per_q = (r["t_match"] + r["t_hough_affine"]) / r["n"]
+        return int(max(16, min(self.args.per_frame, target_s / max(per_q, 1e-9))))
+
+
+# ------------------------------------------------------------------------------------------------
+def measure_int8_cublas_tops(device):
+    """cuBLASLt int8 GEMM rate on this GPU: informational denominator (MEASURED_PEAKS.json has no
+    int8 entry)."""
+    import torch
+    try:
+        a = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=device)
+        b = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=device).t().contiguous().t()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sod_b200.pipeline import DetectionPipeline, ModelDatabase
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU implementation")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    wl = make_workload(args, device)
+    nq, ndb = args.frames * args.per_frame, args.objects * args.kp_per_object
+    db = ModelDatabase(wl["db_des"], wl["m_xy"], wl["m_angle"], wl["m_octave"], wl["m_image"],
+                       wl["img_centroid"], wl["img_size"])
+    pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=device)
+    host = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).pin_memory()
+            for k in ("q_xy", "q_angle", "q_octave", "q_frame")}
+    host["q_des"] = wl["q_des"].cpu().pin_memory()
+    h2d_bytes = int(sum(t.numel() * t.element_size() for t in host.values()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    int8_tops = measure_int8_cublas_tops(device) if rank == 0 else None
+
+    # ---------------- device-resident leg
+    pipe.load_queries(wl["q_des"], host["q_xy"], host["q_angle"], host["q_octave"], host["q_frame"])
+    for _ in range(args.warmup):
+        r = pipe.detect_device(nq)
+    barrier()
+    pipe.matcher.events = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        r = pipe.detect_device(nq)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    match_events, pipe.matcher.events = pipe.matcher.events, None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    match_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in match_events]))], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(match_ms, op=dist.ReduceOp.MAX)
+    ms_total, match_ms = float(ms.item()), float(match_ms.item())
+    res = pipe.fetch(r)
+
+    # ---------------- end-to-end leg: host buffers in, host results out
+    for _ in range(max(1, args.warmup // 2)):
+        out = pipe.detect(host["q_des"], host["q_xy"], host["q_angle"], host["q_octave"], host["q_frame"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = pipe.detect(host["q_des"], host["q_xy"], host["q_angle"], host["q_octave"], host["q_frame"])
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    d2h_bytes = DetectionPipeline.fetched_bytes(out)
+
+    # ---------------- CPU baseline (rank 0, single-GPU run only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(wl, args)
+        n = ref.calibrate(args.cpu_seconds)
+        rr = ref.run(ref.sample_rows(1, n))
+        cpu = {"value": rr["n"] / (rr["t_match"] + rr["t_hough_affine"]), "unit": UNIT, "cores": ref.threads,
+               "kind": "port",
+               "sample": (f"{rr['n']} query descriptors of one frame vs the full {ndb}-row database: "
+                          f"cv2.BFMatcher.knnMatch on {ref.threads} OpenCV threads ({rr['t_match']:.2f} s, the call the "
+                          f"reference makes, database added in <2^18-row chunks) + oracle port of the reference's "
+                          f"single-threaded Python Hough/affine loops ({rr['t_hough_affine']:.2f} s, {rr['matches']} matches)"),
+               "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        bf16_sus = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak = 2.0 * bf16_sus
+        shard_rows = pipe.row_hi - pipe.row_lo
+        ops = 2.0 * nq * shard_rows * 128
+        achieved = ops / (match_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": nq * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": (f"{args.frames} frames x {args.per_frame} query descriptors vs {args.objects} objects x "
+                                    f"{args.kp_per_object} = {ndb} database descriptors (BASELINE configs[3])"),
+                       "n_query": nq, "n_db": ndb, "bins": 15, "ratio": 0.75, "hough_spaces": "per (frame, object)",
+                       "parallelism": f"db-shard{world}+allgather-top2" if world > 1 else "single",
+                       "l2": "inputs larger than L2 (128 MB database + 164 MB queries per step)"},
+            "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": pipe.launches_per_call * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "match_top2_kernel",
+                         "kernel_ms": match_ms,
+                         "peak_source": ("2 x MEASURED_PEAKS.bf16_tflops_sustained (int8 dense = 2 x bf16 dense on B200; "
+                                         "no measured int8 entry)" if peaks else "2 x 1400 TFLOP/s fallback"),
+                         "frac_of_nominal_int8_4500": achieved / 4500.0,
+                         "int8_cublaslt_8192_tops": int8_tops},
+            "result_check": {"matches": res["n_matches"], "bins": res["n_bins"], "valid_bins": res["n_valid"],
+                             "verified_bins": int((res["status"] & 1).sum()), "near_edge": res["n_near_edge"],
+                             "planted": wl["n_true"]},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    wl = make_workload(args, device)   # same synthetic inputs; only data generation touches the GPU
+    ref = CpuReference(wl, args)
+    n = ref.calibrate(args.cpu_seconds)
+    for w in range(args.warmup):
+        ref.run(ref.sample_rows(w, max(16, n // 8)))
+    t0 = time.perf_counter()
+    tot = 0
+    for s in range(args.steps):
+        tot += ref.run(ref.sample_rows(s, n))["n"]
+    dt = time.perf_counter() - t0
+    nq, ndb = args.frames * args.per_frame, args.objects * args.kp_per_object
+    v = tot / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": (f"{args.frames} frames x {args.per_frame} query descriptors vs {args.objects} objects x "
+                                    f"{args.kp_per_object} = {ndb} database descriptors (BASELINE configs[3])"),
+                       "n_query": nq, "n_db": ndb, "bins": 15, "ratio": 0.75},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.threads, "kind": "port", "host_cpus": os.cpu_count(),
+                             "sample": (f"each step = {n} query descriptors of one frame vs the full database: "
+                                        f"cv2.BFMatcher.knnMatch ({ref.threads} threads, chunks < 2^18 rows) + "
+                                        "oracle port of the reference's Python Hough/affine loops (1 thread)")},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--per-frame", type=int, default=5000)
+    ap.add_argument("--objects", type=int, default=1000)
+    ap.add_argument("--kp-per-object", type=int, default=1000)
+    ap.add_argument("--instances", type=int, default=4)
+    ap.add_argument("--inlier-frac", type=float, default=0.10)
+    ap.add_argument("--false-frac", type=float, default=0.01)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

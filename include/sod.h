@@ -137,11 +137,14 @@ typedef struct {
 } sod_hough_out;
 
 /* Stable compaction of the ratio survivors: match_q = query rows with pass != 0 in ascending
- * order, match_t = their nearest database row (main.py:81-86 builds the same list).  n_out is a
- * device int32.  scratch: sod_compact_scratch_bytes(n_query). */
+ * order, match_t = their nearest database row (main.py:81-86 builds the same list).  Only matches
+ * whose database row lies in [t_lo, t_hi) are kept: a rank of a sharded database keeps the matches
+ * of its own model objects (use 0, INT32_MAX for everything).  n_out is a device int32.
+ * scratch: sod_compact_scratch_bytes(n_query). */
 size_t sod_compact_scratch_bytes(int64_t n_query);
-int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t* match_q,
-                        int32_t* match_t, int32_t* n_out, void* scratch, sod_stream_t stream);
+int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t t_lo,
+                        int32_t t_hi, int32_t* match_q, int32_t* match_t, int32_t* n_out,
+                        void* scratch, sod_stream_t stream);
 
 /* estimate_object_pose + calculate_bin_index only (HoughTransformHelperFunctions.py:4-72), no voting:
  * pose [n][4] and base_bin [n] as in sod_hough_out; near_edge may be NULL. */

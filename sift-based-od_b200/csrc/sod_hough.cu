@@ -387,12 +387,18 @@ __global__ void hough_finish_kernel(const FinishArgs a) {
 constexpr int kCompactThreads = 1024;
 
 __global__ void __launch_bounds__(kCompactThreads)
-compact_count_kernel(const uint8_t* __restrict__ pass, int64_t n, int32_t* __restrict__ block_counts) {
+compact_count_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ pass, int64_t n,
+                     int32_t t_lo, int32_t t_hi, int32_t* __restrict__ block_counts) {
   __shared__ int s;
   if (threadIdx.x == 0) s = 0;
   __syncthreads();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kCompactThreads + threadIdx.x;
-  const unsigned b = __ballot_sync(0xffffffffu, i < n && pass[i]);
+  bool keep = i < n && pass[i];
+  if (keep) {
+    const int32_t t = idx[i * 2];
+    keep = t >= t_lo && t < t_hi;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, keep);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s, __popc(b));
   __syncthreads();
   if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
@@ -400,12 +406,17 @@ compact_count_kernel(const uint8_t* __restrict__ pass, int64_t n, int32_t* __res
 
 __global__ void __launch_bounds__(kCompactThreads)
 compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ pass, int64_t n,
-                     const int32_t* __restrict__ block_off, int32_t* __restrict__ match_q,
-                     int32_t* __restrict__ match_t) {
+                     int32_t t_lo, int32_t t_hi, const int32_t* __restrict__ block_off,
+                     int32_t* __restrict__ match_q, int32_t* __restrict__ match_t) {
   __shared__ int warp_base[kCompactThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kCompactThreads + threadIdx.x;
-  const bool keep = i < n && pass[i];
+  bool keep = i < n && pass[i];
+  int32_t t = 0;
+  if (keep) {
+    t = idx[i * 2];
+    keep = t >= t_lo && t < t_hi;
+  }
   const unsigned b = __ballot_sync(0xffffffffu, keep);
   if (lane == 0) warp_base[warp] = __popc(b);
   __syncthreads();
@@ -422,7 +433,7 @@ compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict_
   if (keep) {
     const int pos = block_off[blockIdx.x] + warp_base[warp] + __popc(b & ((1u << lane) - 1u));
     match_q[pos] = static_cast<int32_t>(i);
-    match_t[pos] = idx[i * 2];
+    match_t[pos] = t;
   }
 }
 
@@ -465,8 +476,9 @@ size_t sod_compact_scratch_bytes(int64_t n_query) {
   return static_cast<size_t>(2 * (blocks + 1)) * 4;
 }
 
-int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t* match_q,
-                        int32_t* match_t, int32_t* n_out, void* scratch, sod_stream_t stream) {
+int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query, int32_t t_lo,
+                        int32_t t_hi, int32_t* match_q, int32_t* match_t, int32_t* n_out,
+                        void* scratch, sod_stream_t stream) {
   SOD_CHECK_ARG(n_query >= 0, "n_query < 0");
   SOD_CHECK_ARG(n_out, "null n_out");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -478,12 +490,13 @@ int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query
   const int64_t blocks = (n_query + kCompactThreads - 1) / kCompactThreads;
   int32_t* counts = static_cast<int32_t*>(scratch);
   int32_t* offs = counts + blocks + 1;
-  compact_count_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(pass, n_query, counts);
+  compact_count_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(idx, pass, n_query, t_lo,
+                                                                                  t_hi, counts);
   SOD_CHECK_LAUNCH("compact_count_kernel");
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, blocks, offs, nullptr, n_out);
   SOD_CHECK_LAUNCH("exclusive_scan_kernel");
   compact_write_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(
-      idx, pass, n_query, offs, match_q, match_t);
+      idx, pass, n_query, t_lo, t_hi, offs, match_q, match_t);
   SOD_CHECK_LAUNCH("compact_write_kernel");
   return SOD_OK;
 }

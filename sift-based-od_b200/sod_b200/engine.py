@@ -83,6 +83,7 @@ class Matcher:
         self.shard = shard
         self._ws: torch.Tensor | None = None
         self._qn: torch.Tensor | None = None
+        self.events: list | None = None   # if a list: (start, end) CUDA events around sod_match_top2
 
     def _scratch(self, nq: int) -> tuple[torch.Tensor, torch.Tensor]:
         need = int(lib.sod_match_workspace_bytes(nq, self.shard.n))
@@ -102,9 +103,15 @@ class Matcher:
         d2 = torch.empty((nq, 2), dtype=torch.int32, device=q_u8.device)
         s = self.shard
         check(lib.sod_query_prepare(_ptr(q_u8), nq, _ptr(qn), _stream()), "sod_query_prepare")
+        if self.events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(lib.sod_match_top2(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n, s.index_base,
                                  _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(), _stream()),
               "sod_match_top2")
+        if self.events is not None:
+            e1.record()
+            self.events.append((e0, e1))
         return idx, d2
 
 
@@ -198,8 +205,9 @@ class SceneArrays:
             int(self.img_centroid.shape[0]), self.groups_per_frame)
 
 
-def compact_matches(idx: torch.Tensor, ok: torch.Tensor):
-    """Ratio survivors in query order -> (match_q, match_t, n_dev); stays on the device."""
+def compact_matches(idx: torch.Tensor, ok: torch.Tensor, t_lo: int = 0, t_hi: int = 2 ** 31 - 1):
+    """Ratio survivors (whose database row is in [t_lo, t_hi)) in query order ->
+    (match_q, match_t, n_dev); stays on the device."""
     idx = _require_cuda(idx, torch.int32, "idx")
     ok = _require_cuda(ok, torch.uint8, "pass flags")
     nq = int(ok.shape[0])
@@ -208,8 +216,8 @@ def compact_matches(idx: torch.Tensor, ok: torch.Tensor):
     mt = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
     n = torch.zeros(1, dtype=torch.int32, device=dev)
     scratch = torch.empty(int(lib.sod_compact_scratch_bytes(nq)), dtype=torch.uint8, device=dev)
-    check(lib.sod_compact_matches(_ptr(idx), _ptr(ok), nq, _ptr(mq), _ptr(mt), _ptr(n), _ptr(scratch),
-                                  _stream()), "sod_compact_matches")
+    check(lib.sod_compact_matches(_ptr(idx), _ptr(ok), nq, int(t_lo), int(t_hi), _ptr(mq), _ptr(mt), _ptr(n),
+                                  _ptr(scratch), _stream()), "sod_compact_matches")
     return mq, mt, n
 
 

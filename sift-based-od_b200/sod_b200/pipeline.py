@@ -1,0 +1,147 @@
+"""Array-level public API of the hot path: match -> ratio -> Hough -> affine for a batch of query
+frames against a (possibly sharded) model database.  This is what bench.py and multi-GPU callers
+use; main.Main is the object-level drop-in on top of the same engine.
+
+Multi-GPU: one process per GPU; the database rows are split contiguously and
+object-aligned across ranks, the query batch is replicated, every rank computes shard-local top-2
+with global indices, one all-gather of 16 B per query row exchanges them, sod_top2_merge reproduces
+the single-GPU result (ties included), and each rank runs Hough + affine for the matches of its own
+objects only.  There is no other collective.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import engine as E
+
+
+def shard_bounds(n_objects: int, rows_per_object: np.ndarray | int, rank: int, world: int) -> tuple[int, int, int, int]:
+    """Object-aligned contiguous split -> (obj_lo, obj_hi, row_lo, row_hi) of `rank`."""
+    obj_lo = n_objects * rank // world
+    obj_hi = n_objects * (rank + 1) // world
+    if np.isscalar(rows_per_object):
+        return obj_lo, obj_hi, obj_lo * int(rows_per_object), obj_hi * int(rows_per_object)
+    starts = np.concatenate([[0], np.cumsum(rows_per_object)])
+    return obj_lo, obj_hi, int(starts[obj_lo]), int(starts[obj_hi])
+
+
+@dataclass
+class ModelDatabase:
+    """Host-side description of the model database (what GenerateDatabaseInfo pickles, as arrays)."""
+    des: np.ndarray | torch.Tensor   # u8 [N,128]
+    xy: np.ndarray                   # f32 [N,2]
+    angle: np.ndarray                # f32 [N]
+    octave: np.ndarray               # i32 [N]
+    image: np.ndarray                # i32 [N] model image (= object) of each row, non-decreasing
+    img_centroid: np.ndarray         # f64 [n_images,2]
+    img_size: np.ndarray             # [n_images,2] (w,h)
+
+
+class DetectionPipeline:
+    def __init__(self, db: ModelDatabase, max_queries: int, frame_wh: np.ndarray, rank: int = 0,
+                 world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
+                 affine_threshold: int = 4, per_object_spaces: bool = True, device: str | torch.device = "cuda"):
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device(device)
+        self.bins, self.vote_threshold, self.affine_threshold = bins, vote_threshold, affine_threshold
+        n_images = int(db.img_centroid.shape[0])
+        image = np.asarray(db.image)
+        rows = np.bincount(image, minlength=n_images)
+        if np.any(np.diff(image) < 0):
+            raise ValueError("database rows must be grouped by model image")
+        _, _, self.row_lo, self.row_hi = shard_bounds(n_images, rows, rank, world)
+        des = db.des[self.row_lo:self.row_hi]
+        des_dev = (des if isinstance(des, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(des)))
+        self.shard = E.prepare_db(des_dev.to(self.device).contiguous(), index_base=self.row_lo)
+        self.matcher = E.Matcher(self.shard)
+        self.max_queries = int(max_queries)
+        nq = self.max_queries
+        dev = self.device
+        # query-side device buffers (filled by copy for host inputs, pointers stay stable)
+        self.q_des = torch.empty((nq, 128), dtype=torch.uint8, device=dev)
+        self.scene = E.SceneArrays(
+            torch.zeros((nq, 2), dtype=torch.float32), torch.zeros(nq, dtype=torch.float32),
+            torch.zeros(nq, dtype=torch.int32), db.xy, db.angle, db.octave, db.image, db.img_centroid,
+            np.asarray(db.img_size, np.float64), frame_wh, q_frame=torch.zeros(nq, dtype=torch.int32),
+            img_group=np.arange(n_images, dtype=np.int32) if per_object_spaces else None,
+            groups_per_frame=n_images if per_object_spaces else 1, device=dev)
+        self.voter = E.HoughVoter(self.scene, bins)
+        self._aff: E.AffineResult | None = None
+        if world > 1:
+            self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+        self.launches_per_call = 14  # our kernels per detect_device call
+
+    # ---------------------------------------------------------------- device-resident inputs
+    def load_queries(self, des, xy, angle, octave, frame) -> int:
+        """Copy one batch of query frames (host or device arrays) into the pipeline's buffers."""
+        n = int(des.shape[0])
+        if n > self.max_queries:
+            raise ValueError("batch larger than max_queries")
+        t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(a)  # noqa: E731
+        self.q_des[:n].copy_(t(des), non_blocking=True)
+        self.scene.q_xy[:n].copy_(t(xy), non_blocking=True)
+        self.scene.q_angle[:n].copy_(t(angle), non_blocking=True)
+        self.scene.q_octave[:n].copy_(t(octave), non_blocking=True)
+        self.scene.q_frame[:n].copy_(t(frame), non_blocking=True)
+        return n
+
+    def detect_device(self, n: int):
+        """Run the path on the first n loaded query rows; everything stays on the device."""
+        q = self.q_des[:n]
+        idx, d2 = self.matcher.top2(q)
+        if self.world > 1:
+            import torch.distributed as dist
+            gi, gd = self._gather_idx[:, :n], self._gather_d2[:, :n]
+            if n == self.max_queries:
+                dist.all_gather_into_tensor(gi, idx, group=self.group)
+                dist.all_gather_into_tensor(gd, d2, group=self.group)
+            else:
+                gi = torch.empty((self.world, n, 2), dtype=torch.int32, device=self.device)
+                gd = torch.empty_like(gi)
+                dist.all_gather_into_tensor(gi, idx, group=self.group)
+                dist.all_gather_into_tensor(gd, d2, group=self.group)
+            idx, d2, dist_f, ok = E.merge_top2(gi, gd)
+        else:
+            idx, d2, dist_f, ok = E.merge_top2(idx[None], d2[None])
+        lo, hi = (self.row_lo, self.row_hi) if self.world > 1 else (0, 2 ** 31 - 1)
+        mq, mt, n_dev = E.compact_matches(idx, ok, lo, hi)
+        hough = self.voter.vote(mq, mt, n_dev)
+        if self._aff is None:
+            self._aff = E.AffineResult(hough, self.vote_threshold, self.device)
+        aff = E.affine_verify(self.scene, mq, mt, hough, self.vote_threshold, self.affine_threshold,
+                              result=self._aff)
+        return dict(idx=idx, d2=d2, dist=dist_f, ok=ok, match_q=mq, match_t=mt, n_matches=n_dev,
+                    hough=hough, affine=aff)
+
+    # ---------------------------------------------------------------- host in, host out
+    def detect(self, des, xy, angle, octave, frame) -> dict:
+        """Host buffers in (pinned for full copy speed), host results out."""
+        n = self.load_queries(des, xy, angle, octave, frame)
+        r = self.detect_device(n)
+        return self.fetch(r)
+
+    def fetch(self, r: dict) -> dict:
+        """Device -> host read of one result: matches, counters, verified bins of this rank."""
+        counters = torch.cat([r["n_matches"], r["hough"].counters, r["affine"].counters]).cpu().numpy()
+        n_m, n_bins, n_votes, n_edge, ovf, n_valid, ovf2 = (int(v) for v in counters)
+        if ovf or ovf2:
+            raise RuntimeError("output capacity exceeded")
+        a = r["affine"]
+        out = dict(
+            idx=r["idx"].cpu().numpy(), ok=r["ok"].cpu().numpy(), n_matches=n_m, n_bins=n_bins,
+            n_votes=n_votes, n_near_edge=n_edge, n_valid=n_valid,
+            valid_bin=a.valid_bin[:n_valid].cpu().numpy(), params=a.params[:n_valid].cpu().numpy(),
+            votes=a.votes[:n_valid].cpu().numpy(), status=a.status[:n_valid].cpu().numpy())
+        h = r["hough"]
+        vb = a.valid_bin[:n_valid].long()
+        out["valid_group"] = h.bin_group[vb].cpu().numpy()
+        out["valid_code"] = h.bin_code[vb].cpu().numpy()
+        return out
+
+    @staticmethod
+    def fetched_bytes(out: dict) -> int:
+        return int(sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) + 7 * 4)
