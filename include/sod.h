@@ -30,7 +30,7 @@ extern "C" {
 
 #define SOD_DESC_DIM 128  /* bytes per descriptor row */
 #define SOD_TILE_ROWS 128 /* database rows per MMA tile */
-#define SOD_CQ_TILE_INTS 132 /* int32 per tile in the prepared `cq` array: 128 keys + 4 chunk minima */
+#define SOD_CQ_TILE_INTS 260 /* int32 per tile in `cq`: 128 norms + 4 chunk minima + 128 original rows */
 
 typedef void* sod_stream_t; /* cudaStream_t */
 
@@ -51,12 +51,21 @@ int64_t sod_cq_ints(int64_t n_rows);
 int sod_pack_u8_from_f32(const float* src, int64_t n_rows, uint8_t* dst, int32_t* nonint_flag,
                          sod_stream_t stream);
 
-/* K1 (database side).  Per tile of 128 rows, cq holds 128 packed keys
- * (sum_k db[i][k]^2 << 8) | (i % 128)  (INT32_MAX for rows past the end) followed by the minimum
- * sum of squares of each 32-row chunk (used to prune the epilogue); sod_cq_ints(n_rows) int32 in
- * total.  This is the per-row term of |q-t|^2 = |q|^2 + |t|^2 - 2 q.t that OpenCV recomputes per
- * pair inside cv::batchDistance (called from main.py:71). */
-int sod_db_prepare(const uint8_t* db, int64_t n_rows, int32_t* cq, sod_stream_t stream);
+/* K1 (database side): one-time preparation of a database shard for the matcher.
+ *   db_sorted [ceil(n/128)*128][128]  the rows re-ordered and zero-padded to whole tiles: every
+ *                            tile of 128 rows holds rows of adjacent sum of squares |t|^2 (tiles are
+ *                            stored in a scattered order), rows inside a tile by original index;
+ *   cq [sod_cq_ints(n_rows)] per tile: (|t|^2 << 8 | column) of its 128 rows (|t|^2 = 0x7FFFFF for
+ *                            padding), the minimum |t|^2 of each 32-row chunk (prunes the
+ *                            matcher's epilogue) and the original row of every stored row (-1 for
+ *                            padding).
+ * |t|^2 is the per-row term of |q-t|^2 = |q|^2 + |t|^2 - 2 q.t that OpenCV recomputes per pair in
+ * cv::batchDistance (called from main.py:71).  Matching results are reported in ORIGINAL indices;
+ * the re-ordering is invisible to callers.  workspace: sod_db_prepare_workspace_bytes(n_rows),
+ * 256-byte aligned.  Uses cub::DeviceRadixSort for the one-time sort. */
+size_t sod_db_prepare_workspace_bytes(int64_t n_rows);
+int sod_db_prepare(const uint8_t* db, int64_t n_rows, uint8_t* db_sorted, int32_t* cq, void* workspace,
+                   size_t workspace_bytes, sod_stream_t stream);
 
 /* K1 (query side).  qn[i] = sum_k q[i][k]^2. */
 int sod_query_prepare(const uint8_t* q, int64_t n_rows, int32_t* qn, sod_stream_t stream);
@@ -66,10 +75,10 @@ size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db);
 
 /* K2.  For every query row the two database rows with the smallest squared L2 distance, ascending,
  * ties -> lowest index: the result of cv2.BFMatcher().knnMatch(des_query, des, k=2)
- * (main.py:70-71) with exact integer distances.  out_idx[i][j] = db_index_base + row (or -1 when the
- * database has fewer than j+1 rows), out_d2[i][j] = squared distance (0xFFFFFFFF when idx = -1).
+ * (main.py:70-71) with exact integer distances.  db_sorted / cq come from sod_db_prepare.
+ * out_idx[i][j] = db_index_base + ORIGINAL row (or -1 when the database has fewer than j+1 rows), out_d2[i][j] = squared distance (0xFFFFFFFF when idx = -1).
  * tcgen05 kind::i8 MMA, TMA-fed, top-2 selection fused in the TMEM epilogue. */
-int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db,
+int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
                    const int32_t* cq, int64_t n_db, int32_t db_index_base, int32_t* out_idx,
                    uint32_t* out_d2, void* workspace, size_t workspace_bytes, sod_stream_t stream);
 

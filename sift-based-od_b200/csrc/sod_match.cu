@@ -1,4 +1,4 @@
-// K0-K3: descriptor packing, per-row norms, the tcgen05 2-NN matcher and the top-2 merge.
+// K0-K3: descriptor packing, database preparation, the tcgen05 2-NN matcher and the top-2 merge.
 //
 // Replaces cv2.BFMatcher().knnMatch(des_query, des, k=2) + the ratio loop of the reference
 // (main.py:70-86).  |q-t|^2 = |q|^2 + |t|^2 - 2 q.t with u8 operands is exact in int32, so the
@@ -7,22 +7,25 @@
 //
 // Kernel anatomy (one persistent CTA per SM, 384 threads):
 //   warp 0      TMA producer: query block (2 x 128 rows, double buffered) + database tiles
-//               (128 rows = 16 KB, kStages-deep ring) + the 512 B slice of per-row constants cq.
-//   warp 1      MMA issuer (one thread): per database tile 2 x 4 UTCIMMA (M=128,N=128,K=32) into a
-//               double-buffered TMEM accumulator (2 halves x 2 buffers x 128 columns = 512 columns).
+//               (128 rows = 16 KB, kStages-deep ring) + the 528 B slice of per-row constants.
+//   warp 1      MMA issuer (one thread): per database tile 2 x 4 UTCIMMA (M=128,N=128,K=32) into
+//               four independent 128-column TMEM accumulator slots (2 halves x 2 buffers).
 //   warp 2      TMEM allocator.
-//   warps 4-11  epilogue: thread <-> query row (TMEM lane), sweeps the 128 columns of the tile and
-//               keeps a running top-2 of the packed key  ((|t|^2 - 2 q.t) << 8) | column.
+//   warps 4-11  epilogue: thread <-> query row (TMEM lane).  Pulls the 128 columns of its slot into
+//               registers, releases the slot at once, then prunes: a column can only enter the
+//               row's top-2 if  |t|^2 - 2 q.t  <=  current 2nd best.
 //
-// Packed key.  cq[n] = (|t_n|^2 << 8) | (n & 127) is prepared once per database.  With
-// Q = |q|^2 << 8,  key' = cq - 512*acc  equals  ((d2 << 8) | col) - Q  (mod 2^32).  d2 <= 128*255^2
-// < 2^23 so (d2<<8|col) < 2^31 and Q < 2^31: key' never overflows int32 and the signed order of
-// key' is the (d2, col) lexicographic order -> one IMAD per element, ties resolve to the lowest
-// column.  Across tiles the column byte is cleared before a new tile is compared so that equal
-// distances keep the EARLIER tile (lowest database index, as cv2 does).
+// Pruning needs a bound that is tight PER ROW: a warp takes the slow path as soon as one of its 32
+// rows does.  sod_db_prepare therefore stores the database sorted by |t|^2, so that the smallest
+// |t|^2 of a 32-column chunk (cmin) is within a few units of every member and
+//     cmin - 2 * max_j acc_j  >  2nd best      (one 3-input max tree on the raw accumulators)
+// rejects almost every chunk after the first few thousand columns.  Inside a tile rows are ordered
+// by original index and a permutation maps back, so results (incl. ties -> lowest original index,
+// as cv2) do not depend on the reordering.
 #include <cudaTypedefs.h>
 
 #include <climits>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "sod_common.cuh"
 #include "sod_ptx.cuh"
@@ -40,26 +43,32 @@ constexpr int kBlockQ = kTileM * kHalves;   // 256 query rows per unit
 constexpr int kTileN = SOD_TILE_ROWS;       // database rows per MMA
 constexpr int kTileBytes = kTileN * SOD_DESC_DIM;  // 16 KB (A half-tile has the same size)
 constexpr int kStages = 6;
-constexpr int kCqSlots = kStages + 2;       // see the slot-reuse argument in the producer
+constexpr int kCqSlots = kStages + 4;       // see the slot-reuse argument in the producer
 constexpr int kChunk = 32;                  // accumulator columns per tcgen05.ld
-constexpr int kCqTile = SOD_CQ_TILE_INTS;   // 128 packed keys + 4 per-chunk minima of |t|^2
-constexpr int kCqTileBytes = kCqTile * 4;   // 528 B, a multiple of 16 for the bulk copy
-constexpr int kInitKey = INT_MAX & ~0xFF;   // "no candidate yet", column byte cleared
+constexpr int kCqTile = SOD_CQ_TILE_INTS;   // 128 x |t|^2 + 4 per-chunk minima + 128 x original row
+constexpr int kCqPerm = kTileN + 4;         // offset of the permutation inside a tile's slice
+constexpr int kCqTileBytes = kCqTile * 4;   // 1040 B, a multiple of 16 for the bulk copy
+constexpr int kNoKey = 0x7FFFFF;            // |t|^2 of padding rows / "no candidate yet" (> 128*255^2,
+                                            // and (kNoKey << 8 | 127) still fits int32)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kTmemCols = 512;
+constexpr int kRegsLight = 56;      // producer / MMA / allocator warpgroup after setmaxnreg.dec
+constexpr int kRegsEpilogue = 224;  // epilogue warpgroups: 128 accumulator registers + keys
+static_assert(128 * kRegsLight + kEpiWarps * 32 * kRegsEpilogue <= 65536, "register file");
 
 constexpr int kOffA = 0;                                    // [2 buffers][2 halves][16 KB]
 constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;     // [kStages][16 KB]
 constexpr int kOffCq = kOffB + kStages * kTileBytes;        // [kCqSlots][128] int32
 constexpr int kOffBar = kOffCq + kCqSlots * kCqTileBytes;
-constexpr int kNumBars = 2 * kStages + 8 + kCqSlots;
+constexpr int kNumBars = 2 * kStages + 12 + kCqSlots;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;         // +1024: manual 1 KB alignment
 
 struct MatchArgs {
   const int32_t* qn;   // [nq] |q|^2
-  const int32_t* cq;   // [n_tiles][132] packed per-row constants + chunk minima
+  const int32_t* cq;   // [n_tiles][260] per stored row: |t|^2 << 8 | column, chunk minima of |t|^2,
+                       // original row (-1 = padding)
   uint32_t* part_d2;   // [n_seg][nq][2]
   int32_t* part_idx;   // [n_seg][nq][2]
   int nq;
@@ -69,58 +78,86 @@ struct MatchArgs {
   int idx_base;
 };
 
-// One chunk of 32 accumulator columns -> running top-2, in three levels of increasing cost:
-//  1. bound: every key of the chunk is >= (cmin - 2*max(acc)) << 8 where cmin is the smallest
-//     |t|^2 of the chunk; if that already exceeds the thread's 2nd best nothing can change
-//     (~0.5 ALU op per element: a 3-input max tree on the raw accumulators);
-//  2. exact: compute the 32 packed keys and their minimum (1 IMAD + 0.5 min3 per element);
-//  3. update: the plain running top-2 (3 ops per element) - after the first few thousand columns
-//     of a sweep only a few percent of the chunks get here.
-// All comparisons are exact, so pruning never changes the result.
-__device__ __forceinline__ void top2_chunk(const uint32_t (&v)[32], const int4* __restrict__ cq4,
-                                           int cmin, int& m1, int& m2, bool& touched) {
+// Balanced 3-input reduction trees (depth 4) over 32 registers: the serial form is a 16-deep
+// dependent chain of VIMNMX3, which is latency-bound with two epilogue warps per scheduler.
+__device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
+__device__ __forceinline__ int max_tree32(const int* v) {
+  int t[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) t[i] = imax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  t[10] = max(v[30], v[31]);
+  const int u0 = imax3(t[0], t[1], t[2]), u1 = imax3(t[3], t[4], t[5]), u2 = imax3(t[6], t[7], t[8]);
+  return max(imax3(u0, u1, u2), max(t[9], t[10]));
+}
+__device__ __forceinline__ int min_tree32(const int* v) {
+  int t[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) t[i] = imin3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  t[10] = min(v[30], v[31]);
+  const int u0 = imin3(t[0], t[1], t[2]), u1 = imin3(t[3], t[4], t[5]), u2 = imin3(t[6], t[7], t[8]);
+  return min(imin3(u0, u1, u2), min(t[9], t[10]));
+}
+
+// Running top-2 of one query row as two 64-bit keys (d << 32 | original index), d = d2 - |q|^2:
+// signed 64-bit order is the (distance, index) lexicographic order.
+struct Top2 {
+  long long k1, k2;
+  int d2;  // high word of k2: the pruning threshold
+  __device__ __forceinline__ void offer(int d, int i) {
+    const long long key = (static_cast<long long>(d) << 32) | static_cast<unsigned>(i);
+    if (key < k1) {
+      k2 = k1;
+      k1 = key;
+    } else if (key < k2) {
+      k2 = key;
+    }
+    d2 = static_cast<int>(k2 >> 32);
+  }
+};
+constexpr long long kNoKey64 = (static_cast<long long>(kNoKey) << 32) | 0x7FFFFFFF;
+
+// One chunk of 32 accumulator columns, in three levels of increasing cost:
+//  1. bound: every element has |t|^2 - 2 q.t >= cmin - 2*max(acc); if that exceeds the row's 2nd
+//     best nothing can change (~0.5 ALU op per element, tight because the database is norm-sorted);
+//  2. exact: the 32 packed keys ((|t|^2 - 2 q.t) << 8 | tile column) by one IMAD each from the
+//     prepared (|t|^2 << 8 | column), and their minimum (1.5 ops per element);
+//  3. update: branch-free top-2 of the chunk's packed keys (columns inside a tile are in original-
+//     index order, so ties inside the tile resolve correctly), then at most two offers to the
+//     running best with the ORIGINAL row index read through the permutation in shared memory,
+//     which settles ties across tiles exactly as cv2 does (lowest original index).
+// All tests are exact; pruning never changes the result.
+__device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __restrict__ cp4,
+                                           int cmin, const int32_t* __restrict__ perm_s,
+                                           int idx_base, Top2& best) {
 #if SOD_EXP == 1 || SOD_EXP == 2
   return;
 #endif
-  int amax = static_cast<int>(v[0]);
-#pragma unroll
-  for (int j = 1; j < 32; ++j) amax = max(amax, static_cast<int>(v[j]));
-  // (cmin - 2*amax) is in d2 units relative to |q|^2; m2 >> 8 is the same quantity of the 2nd best.
-  if (cmin - 2 * amax > (m2 >> 8)) return;
+  const int amax = max_tree32(reinterpret_cast<const int*>(v));
+  if (cmin - 2 * amax > best.d2) return;
   int k[32];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int4 c = cq4[j];
+    const int4 c = cp4[j];
     k[4 * j + 0] = c.x - 512 * static_cast<int>(v[4 * j + 0]);
     k[4 * j + 1] = c.y - 512 * static_cast<int>(v[4 * j + 1]);
     k[4 * j + 2] = c.z - 512 * static_cast<int>(v[4 * j + 2]);
     k[4 * j + 3] = c.w - 512 * static_cast<int>(v[4 * j + 3]);
   }
-  int kmin = k[0];
-#pragma unroll
-  for (int j = 1; j < 32; ++j) kmin = min(kmin, k[j]);
-  if (kmin >= m2) return;
-  touched = true;
+  if ((min_tree32(k) >> 8) > best.d2) return;
+  int t1 = INT_MAX, t2 = INT_MAX;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const int t = max(m1, k[j]);
-    m1 = min(m1, k[j]);
-    m2 = min(m2, t);
+    const int t = max(t1, k[j]);
+    t1 = min(t1, k[j]);
+    t2 = min(t2, t);
   }
-}
-
-// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
-// above the wait.
-__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]),
-                 "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]),
-                 "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]),
-                 "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
-                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
-                 "+r"(v[30]), "+r"(v[31])
-               :
-               : "memory");
+  const int o1 = perm_s[t1 & 0xFF];
+  if (o1 >= 0) best.offer(t1 >> 8, idx_base + o1);
+  if ((t2 >> 8) <= best.d2) {
+    const int o2 = perm_s[t2 & 0xFF];
+    if (o2 >= 0) best.offer(t2 >> 8, idx_base + o2);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -139,9 +176,10 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto bar_afull = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
   auto bar_aempty = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
-  auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * kStages + 4 + b); };
-  auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * kStages + 6 + b); };
-  auto bar_cqfull = [&](int s) { return bar0 + 8u * (2 * kStages + 8 + s); };
+  // accumulator slots are tracked per (buffer, half): four independent 128-column slots
+  auto bar_tfull = [&](int b, int h) { return bar0 + 8u * (2 * kStages + 4 + 2 * b + h); };
+  auto bar_tempty = [&](int b, int h) { return bar0 + 8u * (2 * kStages + 8 + 2 * b + h); };
+  auto bar_cqfull = [&](int s) { return bar0 + 8u * (2 * kStages + 12 + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
   if (warp == 0 && lane == 0) {
@@ -156,8 +194,10 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_afull(b), 1);
       mbar_init(bar_aempty(b), 1);
-      mbar_init(bar_tfull(b), 1);
-      mbar_init(bar_tempty(b), kEpiWarps);
+      for (int h = 0; h < kHalves; ++h) {
+        mbar_init(bar_tfull(b, h), 1);
+        mbar_init(bar_tempty(b, h), kEpiWarps / kHalves);
+      }
     }
     for (int s = 0; s < kCqSlots; ++s) mbar_init(bar_cqfull(s), 1);
     fence_mbar_init();
@@ -173,6 +213,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int total_units = a.n_qblocks * a.n_seg;
 
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsLight>();  // this warpgroup hands its registers to the epilogue warpgroups
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -193,10 +235,11 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mbar_wait(bar_empty(s), ph ^ 1u);
           mbar_arrive_expect_tx(bar_full(s), kTileBytes);
           tma_load_2d(base + kOffB + s * kTileBytes, &tmap_db, bar_full(s), 0, t * kTileN);
-          // cq slice rides in its own, deeper ring: stage s is released when the MMA that read it
-          // retires, but the epilogue reads cq up to two accumulator buffers later.  The write of
-          // step j happens after MMA(j-kStages) retired, hence after the epilogue finished step
-          // j-kStages-2; steps j-kStages-1 .. j-1 may still be live -> kStages+2 slots suffice.
+          // cq slice rides in its own, deeper ring: stage s is released when the MMAs that read it
+          // retire, but the epilogue still reads cq after it has handed the accumulator back.
+          // The write for step j happens after MMA(j-kStages) retired; that MMA was issued after
+          // every epilogue warp RELEASED step j-kStages-2, i.e. finished its arithmetic on step
+          // j-kStages-3.  Steps j-kStages-2 .. j-1 may still be live -> kStages+3 slots are needed.
           const uint32_t slot = step % kCqSlots;
           mbar_arrive_expect_tx(bar_cqfull(slot), kCqTileBytes);
           bulk_load_1d(base + kOffCq + slot * kCqTileBytes, a.cq + static_cast<int64_t>(t) * kCqTile,
@@ -220,25 +263,30 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int t = t0; t < t1; ++t, ++step) {
           const uint32_t s = step % kStages, ph = (step / kStages) & 1u;
           const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
-          mbar_wait(bar_tempty(acc), accph ^ 1u);
           mbar_wait(bar_full(s), ph);
-          tc_fence_after();
           const uint64_t bdesc = umma_desc_k128(base + kOffB + s * kTileBytes);
           const uint32_t d0 = tmem_base + acc * (kHalves * kTileN);
+          mbar_wait(bar_tempty(acc, 0), accph ^ 1u);
+          tc_fence_after();
 #pragma unroll
           for (int k = 0; k < SOD_DESC_DIM / 32; ++k)  // K = 32 bytes per UTCIMMA: +2 x 16 B
             umma_i8(d0, adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
+          umma_commit(bar_tfull(acc, 0));  // first half ready for its epilogue warps
+          mbar_wait(bar_tempty(acc, 1), accph ^ 1u);
+          tc_fence_after();
 #pragma unroll
           for (int k = 0; k < SOD_DESC_DIM / 32; ++k)
             umma_i8(d0 + kTileN, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          umma_commit(bar_empty(s));    // database stage free once these MMAs retire
-          umma_commit(bar_tfull(acc));  // accumulator ready for the epilogue
+          umma_commit(bar_tfull(acc, 1));
+          umma_commit(bar_empty(s));  // database stage free once all eight MMAs retire
         }
         umma_commit(bar_aempty(ab));  // query block buffer free
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ------------------------------------------------------------------ epilogue
+    setmaxnreg_inc<kRegsEpilogue>();
     const int e = warp - 4;
     const int h = e >> 2;       // which query half-tile
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
@@ -250,62 +298,37 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
       const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
-      // Between tiles m1/m2 keep their column byte cleared: an equal distance in a later tile
-      // then never displaces an earlier one (lowest database index wins, as in cv2).
-      int m1 = kInitKey, m2 = kInitKey, i1 = -1, i2 = -1;
+      Top2 best{kNoKey64, kNoKey64, kNoKey};
       for (int t = t0; t < t1; ++t, ++step) {
         const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
         const uint32_t slot = step % kCqSlots, cqph = (step / kCqSlots) & 1u;
-        mbar_wait(bar_tfull(acc), accph);
+        mbar_wait(bar_tfull(acc, h), accph);
         mbar_wait(bar_cqfull(slot), cqph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
-        const int4* cq4 = reinterpret_cast<const int4*>(smem + kOffCq + slot * kCqTileBytes);
-        const int4 cmin = cq4[kTileN / 4];  // per-chunk minima of |t|^2
-        const int s1 = m1, s2 = m2;
-        bool touched = false;
-        uint32_t va[32], vb[32];
-#if SOD_EXP == 2
-        for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0;
-#define tmem_ld32(a, b)
-#define tmem_ld_wait_on(a)
-#endif
-        tmem_ld32(taddr, va);
-        tmem_ld_wait_on(va);
-        tmem_ld32(taddr + kChunk, vb);
-        top2_chunk(va, cq4, cmin.x, m1, m2, touched);
-        tmem_ld_wait_on(vb);
-        tmem_ld32(taddr + 2 * kChunk, va);
-        top2_chunk(vb, cq4 + 8, cmin.y, m1, m2, touched);
-        tmem_ld_wait_on(va);
-        tmem_ld32(taddr + 3 * kChunk, vb);
-        top2_chunk(va, cq4 + 16, cmin.z, m1, m2, touched);
-        tmem_ld_wait_on(vb);
-        // Every TMEM read of this accumulator buffer has landed: hand it back to the MMA warp.
+        const int4* c4 = reinterpret_cast<const int4*>(smem + kOffCq + slot * kCqTileBytes);
+        // Pull the whole 128-column row into registers and hand the accumulator slot straight
+        // back to the MMA warp: the tensor pipe never waits for the selection arithmetic.
+        uint32_t v[kTileN];
+        tmem_ld128_wait(taddr, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(acc));
-        top2_chunk(vb, cq4 + 24, cmin.w, m1, m2, touched);
-        if (touched) {
-          // Recover database indices of the entries that changed in this tile.
-          const int tile_base = a.idx_base + t * kTileN;
-          if (m1 != s1) {
-            i2 = (m2 == s1) ? i1 : tile_base + (m2 & 0xFF);
-            i1 = tile_base + (m1 & 0xFF);
-          } else if (m2 != s2) {
-            i2 = tile_base + (m2 & 0xFF);
-          }
-          m1 &= ~0xFF;
-          m2 &= ~0xFF;
-        }
+        if (lane == 0) mbar_arrive(bar_tempty(acc, h));
+        const int4 cmin = c4[kTileN / 4];  // per-chunk minima of |t|^2
+        const int32_t* perm_s = reinterpret_cast<const int32_t*>(c4) + kCqPerm;
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
+        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
+        top2_chunk(v + 2 * kChunk, c4 + 16, cmin.z, perm_s, a.idx_base, best);
+        top2_chunk(v + 3 * kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best);
       }
       if (row < a.nq) {
-        const uint32_t Q = static_cast<uint32_t>(a.qn[row]) << 8;
+        const int qn = a.qn[row];
         const int64_t o = (static_cast<int64_t>(seg) * a.nq + row) * 2;
-        a.part_d2[o + 0] = (i1 >= 0) ? (static_cast<uint32_t>(m1) + Q) >> 8 : 0xFFFFFFFFu;
-        a.part_d2[o + 1] = (i2 >= 0) ? (static_cast<uint32_t>(m2) + Q) >> 8 : 0xFFFFFFFFu;
-        a.part_idx[o + 0] = i1;
-        a.part_idx[o + 1] = i2;
+        const int d1 = static_cast<int>(best.k1 >> 32), d2 = static_cast<int>(best.k2 >> 32);
+        a.part_d2[o + 0] = d1 != kNoKey ? static_cast<uint32_t>(d1 + qn) : 0xFFFFFFFFu;
+        a.part_d2[o + 1] = d2 != kNoKey ? static_cast<uint32_t>(d2 + qn) : 0xFFFFFFFFu;
+        a.part_idx[o + 0] = d1 != kNoKey ? static_cast<int>(best.k1 & 0xFFFFFFFFll) : -1;
+        a.part_idx[o + 1] = d2 != kNoKey ? static_cast<int>(best.k2 & 0xFFFFFFFFll) : -1;
       }
     }
   }
@@ -329,34 +352,105 @@ __global__ void row_sqnorm_kernel(const uint8_t* __restrict__ x, int64_t n_rows,
   if (lane == 0) out[row] = static_cast<int32_t>(s);
 }
 
-// K1 (database side): one CTA of 128 threads per tile of 128 rows, one row per thread (a full
-// 128-byte line each).  Writes the tile's 128 packed keys (|t|^2 << 8 | column; INT_MAX for rows
-// past the end, which can never win) and the minimum |t|^2 of each 32-row chunk.
-__global__ void __launch_bounds__(kTileN)
-db_prepare_kernel(const uint8_t* __restrict__ db, int64_t n_rows, int32_t* __restrict__ cq) {
-  const int64_t tile = blockIdx.x;
-  const int col = threadIdx.x;
-  const int64_t row = tile * kTileN + col;
-  int32_t key = INT_MAX, c = 0x3FFFFFFF;
-  if (row < n_rows) {
-    const uint4* p = reinterpret_cast<const uint4*>(db + row * SOD_DESC_DIM);
-    uint32_t s = 0;
+// K1 (database side), step 1: |t|^2 of every row as a sort key, row index as the value.
+__global__ void db_norm_kernel(const uint8_t* __restrict__ db, int64_t n_rows,
+                               uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const uint4* p = reinterpret_cast<const uint4*>(db + row * SOD_DESC_DIM);
+  uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < SOD_DESC_DIM / 16; ++j) {
-      const uint4 w = __ldg(p + j);
-      s = __dp4a(w.x, w.x, s);
-      s = __dp4a(w.y, w.y, s);
-      s = __dp4a(w.z, w.z, s);
-      s = __dp4a(w.w, w.w, s);
-    }
-    c = static_cast<int32_t>(s);
-    key = static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col));
+  for (int j = 0; j < SOD_DESC_DIM / 16; ++j) {
+    const uint4 w = __ldg(p + j);
+    s = __dp4a(w.x, w.x, s);
+    s = __dp4a(w.y, w.y, s);
+    s = __dp4a(w.z, w.z, s);
+    s = __dp4a(w.w, w.w, s);
   }
+  keys[row] = s;
+  vals[row] = static_cast<int32_t>(row);
+}
+
+// K1 step 3 (after the radix sort by |t|^2): one CTA per tile of 128 sorted rows.  Inside the tile
+// the rows are re-ordered by original index (bitonic sort in shared memory; padding sorts last),
+// then the tile's constants, permutation and descriptor rows are written.
+__global__ void __launch_bounds__(kTileN)
+db_tile_kernel(const uint8_t* __restrict__ db, int64_t n_rows, int64_t n_tiles, int64_t stride,
+               const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals,
+               uint8_t* __restrict__ db_sorted, int32_t* __restrict__ cq) {
+  __shared__ int s_idx[kTileN];
+  __shared__ int s_c[kTileN];
+  // Storage tile `tile` holds the tile of norm rank (tile * stride) mod n_tiles, stride coprime to
+  // n_tiles: a sweep in storage order then samples the norm range evenly instead of ascending
+  // (ascending order would make every tile improve the running minimum - the worst case for pruning).
+  const int64_t tile = blockIdx.x;
+  const int64_t rank = (tile * stride) % n_tiles;
+  const int col = threadIdx.x;
+  const int64_t src_pos = rank * kTileN + col;
+  const int64_t pos = tile * kTileN + col;
+  s_idx[col] = src_pos < n_rows ? vals[src_pos] : INT_MAX;
+  s_c[col] = src_pos < n_rows ? static_cast<int>(keys[src_pos]) : kNoKey;
+  __syncthreads();
+  for (int k = 2; k <= kTileN; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int partner = col ^ j;
+      if (partner > col) {
+        const bool up = (col & k) == 0;
+        const int a = s_idx[col], b = s_idx[partner];
+        if ((a > b) == up) {
+          s_idx[col] = b; s_idx[partner] = a;
+          const int ca = s_c[col];
+          s_c[col] = s_c[partner]; s_c[partner] = ca;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int idx = s_idx[col];
+  const int c = s_c[col];
   int32_t* out = cq + tile * kCqTile;
-  out[col] = key;
+  out[col] = (c << 8) | col;  // packed key base; padding rows: (kNoKey << 8 | col), never selected
+  out[kCqPerm + col] = idx == INT_MAX ? -1 : idx;
+  int cm = c;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
-  if ((col & 31) == 0) out[kTileN + (col >> 5)] = c;
+  for (int o = 16; o > 0; o >>= 1) cm = min(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+  if ((col & 31) == 0) out[kTileN + (col >> 5)] = cm;
+  uint4* dst = reinterpret_cast<uint4*>(db_sorted + pos * SOD_DESC_DIM);
+  if (idx != INT_MAX) {
+    const uint4* src = reinterpret_cast<const uint4*>(db + static_cast<int64_t>(idx) * SOD_DESC_DIM);
+#pragma unroll
+    for (int j = 0; j < SOD_DESC_DIM / 16; ++j) dst[j] = __ldg(src + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < SOD_DESC_DIM / 16; ++j) dst[j] = make_uint4(0, 0, 0, 0);  // padding row
+  }
+}
+
+struct PrepWs {
+  uint32_t *keys_in, *keys_out;
+  int32_t *vals_in, *vals_out;
+  void* cub_temp;
+  size_t cub_bytes, bytes;
+};
+
+PrepWs carve_prep_ws(void* base, int64_t n) {
+  PrepWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o += (bytes + 255) & ~static_cast<size_t>(255);
+    return p;
+  };
+  w.keys_in = static_cast<uint32_t*>(take(n * 4));
+  w.keys_out = static_cast<uint32_t*>(take(n * 4));
+  w.vals_in = static_cast<int32_t*>(take(n * 4));
+  w.vals_out = static_cast<int32_t*>(take(n * 4));
+  w.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
+                                  static_cast<int>(n), 0, 24);
+  w.cub_temp = take(w.cub_bytes);
+  w.bytes = o;
+  return w;
 }
 
 // K0: float32 -> u8 with an integrality check.
@@ -440,7 +534,8 @@ Plan make_plan(int64_t nq, int64_t ndb, int sms) {
     for (int s = 1; s <= max_seg; ++s) {
       const int64_t units = static_cast<int64_t>(p.n_qblocks) * s;
       const int64_t waves = (units + sms - 1) / sms;
-      const int64_t cost = waves * ((p.n_tiles + s - 1) / s + 3);
+      // +24: a unit restarts the pruning threshold, its first ~2k columns run the slow path
+      const int64_t cost = waves * ((p.n_tiles + s - 1) / s + 24);
       if (best < 0 || cost < best) {
         best = cost;
         p.n_seg = s;
@@ -511,15 +606,37 @@ int sod_pack_u8_from_f32(const float* src, int64_t n_rows, uint8_t* dst, int32_t
   return SOD_OK;
 }
 
-int sod_db_prepare(const uint8_t* db, int64_t n_rows, int32_t* cq, sod_stream_t stream) {
+size_t sod_db_prepare_workspace_bytes(int64_t n_rows) {
+  if (n_rows <= 0) return 256;
+  return carve_prep_ws(nullptr, n_rows).bytes + 256;
+}
+
+int sod_db_prepare(const uint8_t* db, int64_t n_rows, uint8_t* db_sorted, int32_t* cq, void* workspace,
+                   size_t workspace_bytes, sod_stream_t stream) {
   SOD_CHECK_ARG(n_rows >= 0 && n_rows < (int64_t(1) << 31) - kTileN, "n_rows out of range");
   if (n_rows == 0) return SOD_OK;
-  SOD_CHECK_ARG(db && cq, "null pointer");
-  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(db) & 15) == 0, "db must be 16-byte aligned");
+  SOD_CHECK_ARG(db && db_sorted && cq && workspace, "null pointer");
+  SOD_CHECK_ARG(db != db_sorted, "db_sorted must not alias db");
+  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(db) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_sorted) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                "db/db_sorted must be 16-byte and workspace 256-byte aligned");
+  PrepWs w = carve_prep_ws(workspace, n_rows);
+  SOD_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 128;
+  db_norm_kernel<<<static_cast<unsigned>((n_rows + threads - 1) / threads), threads, 0, st>>>(
+      db, n_rows, w.keys_in, w.vals_in);
+  SOD_CHECK_LAUNCH("db_norm_kernel");
+  // |t|^2 <= 128*255^2 < 2^24; LSD radix sort is stable, so equal norms stay in index order.
+  SOD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, w.cub_bytes, w.keys_in, w.keys_out, w.vals_in,
+                                                 w.vals_out, static_cast<int>(n_rows), 0, 24, st));
   const int64_t tiles = (n_rows + kTileN - 1) / kTileN;
-  db_prepare_kernel<<<static_cast<unsigned>(tiles), kTileN, 0, static_cast<cudaStream_t>(stream)>>>(
-      db, n_rows, cq);
-  SOD_CHECK_LAUNCH("db_prepare_kernel");
+  int64_t stride = static_cast<int64_t>(0.6180339887498949 * static_cast<double>(tiles)) | 1;
+  auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+  while (gcd(stride, tiles) != 1) stride += 2;
+  db_tile_kernel<<<static_cast<unsigned>(tiles), kTileN, 0, st>>>(db, n_rows, tiles, stride, w.keys_out,
+                                                                 w.vals_out, db_sorted, cq);
+  SOD_CHECK_LAUNCH("db_tile_kernel");
   return SOD_OK;
 }
 
@@ -542,7 +659,7 @@ size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db) {
   return static_cast<size_t>(p.n_seg) * static_cast<size_t>(n_query) * 2 * 8 + 16;
 }
 
-int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db,
+int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
                    const int32_t* cq, int64_t n_db, int32_t db_index_base, int32_t* out_idx,
                    uint32_t* out_d2, void* workspace, size_t workspace_bytes, sod_stream_t stream) {
   SOD_CHECK_ARG(n_query >= 0 && n_db >= 0, "negative size");
@@ -561,6 +678,7 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
     SOD_CHECK_LAUNCH("top2_merge_kernel");
     return SOD_OK;
   }
+  const uint8_t* db = db_sorted;
   SOD_CHECK_ARG(q && qn && db && cq && workspace, "null pointer");
   SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(db) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(cq) & 15) == 0 &&
@@ -575,7 +693,7 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   CUtensorMap map_q, map_db;
   int rc = make_desc_map(&map_q, q, n_query);
   if (rc != SOD_OK) return rc;
-  rc = make_desc_map(&map_db, db, n_db);
+  rc = make_desc_map(&map_db, db, (n_db + kTileN - 1) / kTileN * kTileN);  // stored padded to whole tiles
   if (rc != SOD_OK) return rc;
 
   MatchArgs a;

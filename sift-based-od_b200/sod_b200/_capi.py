@@ -67,7 +67,8 @@ _PROTOS = {
     "sod_device_sm_count": (C.c_int, []),
     "sod_cq_ints": (_i64, [_i64]),
     "sod_pack_u8_from_f32": (C.c_int, [_p, _i64, _p, _p, _p]),
-    "sod_db_prepare": (C.c_int, [_p, _i64, _p, _p]),
+    "sod_db_prepare_workspace_bytes": (C.c_size_t, [_i64]),
+    "sod_db_prepare": (C.c_int, [_p, _i64, _p, _p, _p, C.c_size_t, _p]),
     "sod_query_prepare": (C.c_int, [_p, _i64, _p, _p]),
     "sod_match_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "sod_match_top2": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p, C.c_size_t, _p]),

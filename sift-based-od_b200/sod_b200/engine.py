@@ -59,21 +59,27 @@ def pack_descriptors(des, device: torch.device | str = "cuda") -> torch.Tensor:
 @dataclass
 class DescriptorShard:
     """A contiguous slice of the model-descriptor database resident in HBM."""
-    des: torch.Tensor        # u8 [n,128]
-    cq: torch.Tensor         # int32 [padded n] packed |t|^2 (sod_db_prepare)
-    index_base: int          # global index of row 0
+    des: torch.Tensor        # u8 [tiles*128,128]: rows re-ordered by sod_db_prepare, zero padded
+    n_rows: int              # number of real rows
+    cq: torch.Tensor         # int32 per tile: |t|^2, chunk minima, original rows
+    index_base: int          # global index of original row 0
 
     @property
     def n(self) -> int:
-        return int(self.des.shape[0])
+        return self.n_rows
 
 
 def prepare_db(des_u8: torch.Tensor, index_base: int = 0) -> DescriptorShard:
     des_u8 = _require_cuda(des_u8, torch.uint8, "database descriptors")
     n = int(des_u8.shape[0])
-    cq = torch.empty(max(int(lib.sod_cq_ints(n)), 1), dtype=torch.int32, device=des_u8.device)
-    check(lib.sod_db_prepare(_ptr(des_u8), n, _ptr(cq), _stream()), "sod_db_prepare")
-    return DescriptorShard(des_u8, cq, int(index_base))
+    dev = des_u8.device
+    tiles = (n + _capi.TILE_ROWS - 1) // _capi.TILE_ROWS
+    cq = torch.empty(max(int(lib.sod_cq_ints(n)), 1), dtype=torch.int32, device=dev)
+    des_sorted = torch.empty((max(tiles * _capi.TILE_ROWS, 1), _capi.DESC_DIM), dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(lib.sod_db_prepare_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    check(lib.sod_db_prepare(_ptr(des_u8), n, _ptr(des_sorted), _ptr(cq), _ptr(ws), ws.numel(),
+                             _stream()), "sod_db_prepare")
+    return DescriptorShard(des_sorted, n, cq, int(index_base))
 
 
 class Matcher:
@@ -106,8 +112,8 @@ class Matcher:
         if self.events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.sod_match_top2(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n, s.index_base,
-                                 _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(), _stream()),
+        check(lib.sod_match_top2(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n,
+                                 s.index_base, _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(), _stream()),
               "sod_match_top2")
         if self.events is not None:
             e1.record()

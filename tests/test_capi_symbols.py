@@ -35,8 +35,8 @@ def test_error_reporting_without_gpu():
     from sod_b200 import _capi
     lib = _capi.lib
     assert lib.sod_version() >= 1000
-    assert lib.sod_cq_ints(0) == 0 and lib.sod_cq_ints(1) == 132 and lib.sod_cq_ints(129) == 264
-    rc = lib.sod_db_prepare(None, -1, None, None)
+    assert lib.sod_cq_ints(0) == 0 and lib.sod_cq_ints(1) == 260 and lib.sod_cq_ints(129) == 520
+    rc = lib.sod_db_prepare(None, -1, None, None, None, 0, None)
     assert rc == -1 and b"n_rows" in lib.sod_last_error()
     rc = lib.sod_top2_merge(None, None, 1, 10, None, None, None, None, 0.75, None)
     assert rc == -1 and b"null" in lib.sod_last_error()
