@@ -5,15 +5,16 @@
 // contraction q.t runs on the 5th-gen tensor cores (tcgen05.mma kind::i8, u8 x u8 -> s32 in TMEM)
 // and the top-2 selection happens in the TMEM epilogue without ever writing distances to HBM.
 //
-// Kernel anatomy (one persistent CTA per SM, 384 threads):
+// Kernel anatomy (one persistent CTA per SM, 640 threads):
 //   warp 0      TMA producer: query block (2 x 128 rows, double buffered) + database tiles
 //               (128 rows = 16 KB, kStages-deep ring) + the 528 B slice of per-row constants.
-//   warp 1      MMA issuer (one thread): per database tile 2 x 4 UTCIMMA (M=128,N=128,K=32) into
-//               four independent 128-column TMEM accumulator slots (2 halves x 2 buffers).
+//   warps 1, 3  MMA issuers, one per query half: per database tile 4 UTCIMMA (M=128,N=128,K=32)
+//               each into four independent 128-column TMEM accumulator slots (2 halves x 2 buffers).
 //   warp 2      TMEM allocator.
-//   warps 4-11  epilogue: thread <-> query row (TMEM lane).  Pulls the 128 columns of its slot into
-//               registers, releases the slot at once, then prunes: a column can only enter the
-//               row's top-2 if  |t|^2 - 2 q.t  <=  current 2nd best.
+//   warps 4-19  epilogue: thread <-> query row (TMEM lane), 16 warps = 4 lane quadrants x 2 query
+//               halves x 2 column halves.  A warp pulls its 64 columns of the slot into registers,
+//               releases the slot at once, and prunes: a column can only enter the row's top-2 if
+//               |t|^2 - 2 q.t  <=  current 2nd best.  (Two threads per row: two candidate lists.)
 //
 // Pruning needs a bound that is tight PER ROW: a warp takes the slow path as soon as one of its 32
 // rows does.  sod_db_prepare therefore stores the database sorted by |t|^2, so that the smallest
@@ -30,6 +31,13 @@
 #include "sod_common.cuh"
 #include "sod_ptx.cuh"
 
+// Epilogue organisation (compile-time experiment switch; all three give identical results):
+//   1 = 8 warps: (lane quadrant x query half), 128 columns per tile, slot released right after the load
+//   2 = 16 warps: as 1 but split by tile parity (every other tile each), two 64-column loads
+//   3 = 16 warps: split by column half (64 columns of every tile each)
+#ifndef SOD_EPI_MODE
+#define SOD_EPI_MODE 2
+#endif
 #ifndef SOD_EXP
 #define SOD_EXP 0  // kernel experiments (timing only, results invalid): 1 = no epilogue math, 2 = no TMEM loads
 #endif
@@ -50,12 +58,17 @@ constexpr int kCqPerm = kTileN + 4;         // offset of the permutation inside 
 constexpr int kCqTileBytes = kCqTile * 4;   // 1040 B, a multiple of 16 for the bulk copy
 constexpr int kNoKey = 0x7FFFFF;            // |t|^2 of padding rows / "no candidate yet" (> 128*255^2,
                                             // and (kNoKey << 8 | 127) still fits int32)
-constexpr int kEpiWarps = 8;
+constexpr int kParity = SOD_EPI_MODE == 1 ? 1 : 2;  // candidate lists per row and segment
+constexpr int kEpiWarps = 4 * kHalves * kParity;    // (TMEM lane quadrant) x (query half) x (split)
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kRegsLight = 56;      // producer / MMA / allocator warpgroup after setmaxnreg.dec
-constexpr int kRegsEpilogue = 224;  // epilogue warpgroups: 128 accumulator registers + keys
-static_assert(128 * kRegsLight + kEpiWarps * 32 * kRegsEpilogue <= 65536, "register file");
+constexpr int kRegsEpilogue = SOD_EPI_MODE == 1 ? 224 : 104;  // accumulator registers + 32 keys + state
+// setmaxnreg only moves registers inside the CTA's launch allocation (threads x launch registers,
+// the latter a multiple of 8): asking for more makes setmaxnreg.inc wait forever.
+constexpr int kRegsLaunch = 65536 / kThreads / 8 * 8;
+static_assert(128 * kRegsLight + kEpiWarps * 32 * kRegsEpilogue <= kThreads * kRegsLaunch,
+              "setmaxnreg budget exceeds the CTA's register pool");
 
 constexpr int kOffA = 0;                                    // [2 buffers][2 halves][16 KB]
 constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;     // [kStages][16 KB]
@@ -69,8 +82,8 @@ struct MatchArgs {
   const int32_t* qn;   // [nq] |q|^2
   const int32_t* cq;   // [n_tiles][260] per stored row: |t|^2 << 8 | column, chunk minima of |t|^2,
                        // original row (-1 = padding)
-  uint32_t* part_d2;   // [n_seg][nq][2]
-  int32_t* part_idx;   // [n_seg][nq][2]
+  uint32_t* part_d2;   // [n_seg * 2][nq][2]  (one list per segment and column half)
+  int32_t* part_idx;   // [n_seg * 2][nq][2]
   int nq;
   int n_tiles;
   int n_qblocks;
@@ -189,14 +202,14 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), kHalves);  // one tcgen05.commit per issuing warp
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_afull(b), 1);
-      mbar_init(bar_aempty(b), 1);
+      mbar_init(bar_aempty(b), kHalves);
       for (int h = 0; h < kHalves; ++h) {
         mbar_init(bar_tfull(b, h), 1);
-        mbar_init(bar_tempty(b, h), kEpiWarps / kHalves);
+        mbar_init(bar_tempty(b, h), SOD_EPI_MODE == 3 ? 8 : 4);  // warps that read one slot
       }
     }
     for (int s = 0; s < kCqSlots; ++s) mbar_init(bar_cqfull(s), 1);
@@ -247,49 +260,52 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_u8(kTileM, kTileN);
-      uint32_t step = 0, ucount = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
-        const int seg = u / a.n_qblocks;
-        const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
-        const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
-        const uint32_t ab = ucount & 1u, aph = (ucount >> 1) & 1u;
-        mbar_wait(bar_afull(ab), aph);
-        const uint64_t adesc0 = umma_desc_k128(base + kOffA + (ab * kHalves + 0) * kTileBytes);
-        const uint64_t adesc1 = umma_desc_k128(base + kOffA + (ab * kHalves + 1) * kTileBytes);
-        for (int t = t0; t < t1; ++t, ++step) {
-          const uint32_t s = step % kStages, ph = (step / kStages) & 1u;
-          const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
-          mbar_wait(bar_full(s), ph);
-          const uint64_t bdesc = umma_desc_k128(base + kOffB + s * kTileBytes);
-          const uint32_t d0 = tmem_base + acc * (kHalves * kTileN);
-          mbar_wait(bar_tempty(acc, 0), accph ^ 1u);
-          tc_fence_after();
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuers
+    // Two issuing warps, one per query half (warp 1 -> half 0, warp 3 -> half 1): with K = 128 an
+    // accumulator slot holds only 256 clk of tensor work, so the issuing warp's own instruction
+    // stream and barrier round trips must stay well below that per slot.  Each warp runs its loop
+    // convergently so that addresses, phases and descriptors live in uniform registers; only the
+    // tcgen05 instructions are issued by one elected lane.  (Inside a divergent `if (lane == 0)`
+    // every UTCIMMA operand needs an R2UR move.)
+    const int h = warp >> 1;
+    constexpr uint32_t idesc = umma_idesc_u8(kTileM, kTileN);
+    uint32_t step = 0, ucount = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
+      const int seg = u / a.n_qblocks;
+      const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
+      const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
+      const uint32_t ab = ucount & 1u, aph = (ucount >> 1) & 1u;
+      mbar_wait(bar_afull(ab), aph);
+      const uint64_t adesc = umma_desc_k128(base + kOffA + (ab * kHalves + h) * kTileBytes);
+      for (int t = t0; t < t1; ++t, ++step) {
+        const uint32_t s = step % kStages, ph = (step / kStages) & 1u;
+        const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
+        const uint64_t bdesc = umma_desc_k128(base + kOffB + s * kTileBytes);
+        const uint32_t d = tmem_base + acc * (kHalves * kTileN) + h * kTileN;
+        mbar_wait(bar_full(s), ph);
+        mbar_wait(bar_tempty(acc, h), accph ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < SOD_DESC_DIM / 32; ++k)  // K = 32 bytes per UTCIMMA: +2 x 16 B
-            umma_i8(d0, adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          umma_commit(bar_tfull(acc, 0));  // first half ready for its epilogue warps
-          mbar_wait(bar_tempty(acc, 1), accph ^ 1u);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < SOD_DESC_DIM / 32; ++k)
-            umma_i8(d0 + kTileN, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          umma_commit(bar_tfull(acc, 1));
-          umma_commit(bar_empty(s));  // database stage free once all eight MMAs retire
+            umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+          umma_commit(bar_tfull(acc, h));  // this half is ready for its epilogue warps
+          umma_commit(bar_empty(s));       // (count 2) database stage free once both halves retire
         }
-        umma_commit(bar_aempty(ab));  // query block buffer free
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(bar_aempty(ab));  // (count 2) query block buffer free
+      __syncwarp();
     }
   }
   } else {
     // ------------------------------------------------------------------ epilogue
     setmaxnreg_inc<kRegsEpilogue>();
     const int e = warp - 4;
-    const int h = e >> 2;       // which query half-tile
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int h = (e >> 2) & 1;         // which query half-tile
+    const uint32_t par = e >> 3;        // which 64-column half of every tile
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t step = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -300,30 +316,68 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
       Top2 best{kNoKey64, kNoKey64, kNoKey};
       for (int t = t0; t < t1; ++t, ++step) {
+#if SOD_EPI_MODE == 2
+        if ((step & 1u) != par) continue;
+#endif
         const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
         const uint32_t slot = step % kCqSlots, cqph = (step / kCqSlots) & 1u;
+        mbar_wait(bar_cqfull(slot), cqph);  // landed long ago: returns at the first poll
         mbar_wait(bar_tfull(acc, h), accph);
-        mbar_wait(bar_cqfull(slot), cqph);
         tc_fence_after();
+        const int32_t* cs = reinterpret_cast<const int32_t*>(smem + kOffCq + slot * kCqTileBytes);
+        const int32_t* perm_s = cs + kCqPerm;
+#if SOD_EPI_MODE == 1
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
-        const int4* c4 = reinterpret_cast<const int4*>(smem + kOffCq + slot * kCqTileBytes);
-        // Pull the whole 128-column row into registers and hand the accumulator slot straight
-        // back to the MMA warp: the tensor pipe never waits for the selection arithmetic.
+        const int4* c4 = reinterpret_cast<const int4*>(cs);
+        const int4 cmin = c4[kTileN / 4];
         uint32_t v[kTileN];
+#if SOD_EXP != 2
         tmem_ld128_wait(taddr, v);
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(acc, h));
-        const int4 cmin = c4[kTileN / 4];  // per-chunk minima of |t|^2
-        const int32_t* perm_s = reinterpret_cast<const int32_t*>(c4) + kCqPerm;
         top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
         top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
         top2_chunk(v + 2 * kChunk, c4 + 16, cmin.z, perm_s, a.idx_base, best);
         top2_chunk(v + 3 * kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best);
+#elif SOD_EPI_MODE == 2
+        const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
+        const int4* c4 = reinterpret_cast<const int4*>(cs);
+        const int4 cmin = c4[kTileN / 4];
+        uint32_t v[2 * kChunk];
+#if SOD_EXP != 2
+        tmem_ld64_wait(taddr, v);
+#endif
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
+        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
+#if SOD_EXP != 2
+        tmem_ld64_wait(taddr + 2 * kChunk, v);
+#endif
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(acc, h));
+        top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best);
+        top2_chunk(v + kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best);
+#else
+        const uint32_t taddr =
+            tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN + par * (2 * kChunk);
+        uint32_t v[2 * kChunk];
+#if SOD_EXP != 2
+        tmem_ld64_wait(taddr, v);
+#endif
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(acc, h));
+        const int4* c4 = reinterpret_cast<const int4*>(cs) + par * 16;
+        const int2 cmin = *reinterpret_cast<const int2*>(cs + kTileN + par * 2);
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
+        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
+#endif
       }
       if (row < a.nq) {
         const int qn = a.qn[row];
-        const int64_t o = (static_cast<int64_t>(seg) * a.nq + row) * 2;
+        const int64_t o = ((static_cast<int64_t>(seg) * kParity + par) * a.nq + row) * 2;
         const int d1 = static_cast<int>(best.k1 >> 32), d2 = static_cast<int>(best.k2 >> 32);
         a.part_d2[o + 0] = d1 != kNoKey ? static_cast<uint32_t>(d1 + qn) : 0xFFFFFFFFu;
         a.part_d2[o + 1] = d2 != kNoKey ? static_cast<uint32_t>(d2 + qn) : 0xFFFFFFFFu;
@@ -656,7 +710,7 @@ size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db) {
   if (n_query <= 0 || n_db <= 0) return 16;
   const int sms = device_sm_count();
   const Plan p = make_plan(n_query, n_db, sms > 0 ? sms : 148);
-  return static_cast<size_t>(p.n_seg) * static_cast<size_t>(n_query) * 2 * 8 + 16;
+  return static_cast<size_t>(p.n_seg) * kParity * static_cast<size_t>(n_query) * 2 * 8 + 16;
 }
 
 int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
@@ -687,7 +741,7 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   const int sms = device_sm_count();
   if (sms <= 0) return SOD_ERR_CUDA;
   const Plan p = make_plan(n_query, n_db, sms);
-  const size_t need = static_cast<size_t>(p.n_seg) * static_cast<size_t>(n_query) * 2 * 8;
+  const size_t need = static_cast<size_t>(p.n_seg) * kParity * static_cast<size_t>(n_query) * 2 * 8;
   SOD_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
 
   CUtensorMap map_q, map_db;
@@ -700,7 +754,7 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   a.qn = qn;
   a.cq = cq;
   a.part_d2 = static_cast<uint32_t*>(workspace);
-  a.part_idx = reinterpret_cast<int32_t*>(a.part_d2 + static_cast<size_t>(p.n_seg) * n_query * 2);
+  a.part_idx = reinterpret_cast<int32_t*>(a.part_d2 + static_cast<size_t>(p.n_seg) * kParity * n_query * 2);
   a.nq = static_cast<int>(n_query);
   a.n_tiles = p.n_tiles;
   a.n_qblocks = p.n_qblocks;
@@ -715,8 +769,8 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   }
   match_top2_kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
   SOD_CHECK_LAUNCH("match_top2_kernel");
-  top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(a.part_idx, a.part_d2, p.n_seg, n_query, out_idx,
-                                                  out_d2, nullptr, nullptr, 0.0);
+  top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(a.part_idx, a.part_d2, p.n_seg * kParity, n_query,
+                                                  out_idx, out_d2, nullptr, nullptr, 0.0);
   SOD_CHECK_LAUNCH("top2_merge_kernel");
   return SOD_OK;
 }
