@@ -322,6 +322,13 @@ def run_ours(args):
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
+        traffic = None
+        try:  # dram__bytes_read+write of one match_top2 launch, from the committed ncu --set full capture
+            tj = json.loads((ROOT / "profiles" / "r01_match_top2_traffic.json").read_text())
+            if world == 1 and (args.frames, args.per_frame, args.objects, args.kp_per_object) == (256, 5000, 1000, 1000):
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         bf16_sus = peaks.get("bf16_tflops_sustained", 1400.0)
         peak = 2.0 * bf16_sus
         shard_rows = pipe.row_hi - pipe.row_lo
@@ -342,7 +349,9 @@ def run_ours(args):
             "gpu_launches": pipe.launches_per_call * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "match_top2_kernel",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "match_top2_kernel",
+                         "algorithmic": {"ops": ops, "definition": "2 * n_query * n_db_shard * 128 int8 ops per launch",
+                                         "min_bytes": nq * 128 + shard_rows * 128},
                          "kernel_ms": match_ms,
                          "peak_source": ("2 x MEASURED_PEAKS.bf16_tflops_sustained (int8 dense = 2 x bf16 dense on B200; "
                                          "no measured int8 entry)" if peaks else "2 x 1400 TFLOP/s fallback"),
