@@ -1,0 +1,104 @@
+"""Parity at BASELINE.json's configuration sizes: C2 against the oracle directly,
+C3/C4-sized databases through size-independent properties (shard-merge invariance, sampled rows
+against the oracle), C5 Hough stress against the oracle's vectorised bin counts."""
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from oracle import sod_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _sift_like_gpu(n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((n, 128), device="cuda", generator=g).abs_()
+    x /= x.norm(dim=1, keepdim=True)
+    x.clamp_(max=0.2)
+    x /= x.norm(dim=1, keepdim=True)
+    return (x * 512).round_().clamp_(0, 255).to(torch.uint8)
+
+
+def test_c2_10k_x_100k_exact_vs_oracle():
+    """configs[1]: 10k queries x 100k database, 10 % planted matches, 0.1 % duplicate rows."""
+    from sod_b200 import engine as E
+    rng = np.random.default_rng(100)
+    db = scenes.sift_like(rng, 100_000)
+    q = scenes.sift_like(rng, 10_000)
+    hit = rng.choice(10_000, 1000, replace=False)
+    src = rng.integers(0, 100_000, 1000)
+    q[hit] = np.clip(db[src].astype(np.int16) + rng.integers(-3, 4, (1000, 128)), 0, 255).astype(np.uint8)
+    dup = rng.integers(0, 100_000, (100, 2))
+    db[dup[:, 1]] = db[dup[:, 0]]
+    idx, d2, dist, ok = E.knn_match_ratio(torch.from_numpy(q).cuda(), E.Matcher(E.prepare_db(torch.from_numpy(db).cuda())))
+    ridx, rd2 = O.knn2(q, db)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
+    np.testing.assert_array_equal(d2.cpu().numpy().astype(np.int64), rd2)
+    np.testing.assert_array_equal(ok.cpu().numpy().astype(bool), O.ratio_pass(rd2, ridx))
+    assert ok.cpu().numpy()[hit].mean() > 0.95
+
+
+def test_c3_1m_database_shard_invariance_and_sampled_rows():
+    """configs[2]: 1M-row database.  (a) the top-2 of 8 object-aligned shards merged equals the top-2
+    of the whole database, bit for bit; (b) 64 sampled query rows equal the oracle."""
+    from sod_b200 import engine as E
+    n, nq = 1_000_000, 10_000
+    db = _sift_like_gpu(n, 101)
+    q = _sift_like_gpu(nq, 102)
+    src = torch.randint(0, n, (1000,), device="cuda")
+    q[:1000] = (db[src].to(torch.int16) + torch.randint(-3, 4, (1000, 128), device="cuda", dtype=torch.int16)).clamp_(0, 255).to(torch.uint8)
+    db[123_456] = db[7]                                   # a tie across shards
+    q[1000] = db[7]
+    whole_idx, whole_d2 = E.Matcher(E.prepare_db(db)).top2(q)
+    parts_i, parts_d = [], []
+    for r in range(8):
+        lo, hi = r * 125_000, (r + 1) * 125_000
+        i, d = E.Matcher(E.prepare_db(db[lo:hi].contiguous(), index_base=lo)).top2(q)
+        parts_i.append(i)
+        parts_d.append(d)
+    mi, md, _, ok = E.merge_top2(torch.stack(parts_i), torch.stack(parts_d))
+    assert torch.equal(mi, whole_idx) and torch.equal(md, whole_d2)
+    assert mi[1000].tolist() == [7, 123_456] and md[1000].tolist() == [0, 0]
+    assert int(ok[:1000].sum()) > 950
+    rows = np.r_[np.arange(0, 32), np.arange(1000, 1032)]
+    ridx, rd2 = O.knn2(q[rows].cpu().numpy(), db.cpu().numpy(), chunk=16)
+    np.testing.assert_array_equal(whole_idx.cpu().numpy()[rows], ridx)
+    np.testing.assert_array_equal(whole_d2.cpu().numpy().astype(np.int64)[rows], rd2)
+
+
+def test_c5_hough_stress_2m_matches_bin_counts():
+    """configs[4]: 2M ratio-passing matches, 500 objects, 90 % outliers: bin -> votes identical to the
+    oracle's vectorised restatement; vote conservation; affine survivors contain the planted pose."""
+    from sod_b200 import engine as E
+    d = scenes.make_match_stress(103)
+    bins = 15
+    sc = E.SceneArrays(d["q_xy"], d["q_angle"], d["q_octave"], d["m_xy"], d["m_angle"], d["m_octave"], d["m_image"],
+                       d["img_centroid"], d["img_size"].astype(np.float64),
+                       np.array([[d["width"], d["height"]]], np.int32), img_group=d["img_group"],
+                       groups_per_frame=500)
+    mq = torch.from_numpy(d["match_q"]).cuda()
+    mt = torch.from_numpy(d["match_t"]).cuda()
+    res = E.HoughVoter(sc, bins).vote(mq, mt)
+    aff = E.affine_verify(sc, mq, mt, res, 5, 4)
+    c = res.counters.cpu().numpy()
+    nb, nv = int(c[0]), int(c[1])
+    assert c[3] == 0 and c[2] == 0
+    osc = O.Scene(d["q_xy"], d["q_angle"], d["q_octave"], d["m_xy"], d["m_angle"], d["m_octave"], d["m_image"],
+                  d["img_centroid"], d["img_size"], d["width"], d["height"], d["img_group"])
+    _, base = O.hough_base_bins_vectorized(osc, d["match_q"], d["match_t"], bins)
+    keys, counts = O.vote_counts_vectorized(base, d["img_group"][d["m_image"][d["match_t"]]], bins)
+    got = res.bin_group[:nb].cpu().numpy().astype(np.int64) * bins ** 4 + res.bin_code[:nb].cpu().numpy()
+    o = np.argsort(got)
+    np.testing.assert_array_equal(got[o], keys)
+    np.testing.assert_array_equal(res.bin_count[:nb].cpu().numpy()[o], counts)
+    assert nv == int(counts.sum())
+    # members are a permutation-free CSR: every bin's list is strictly ascending
+    off = res.bin_offset[:nb].cpu().numpy()
+    mem = res.members[:nv].cpu().numpy()
+    big = np.argsort(-res.bin_count[:nb].cpu().numpy())[:200]
+    for b in big:
+        m = mem[off[b]:off[b] + res.bin_count[b].item()]
+        assert (np.diff(m) > 0).all()
+    a = aff.host(nv)
+    assert a["live"].sum() >= 400            # ~one verified bin per object at least
