@@ -26,6 +26,7 @@ constexpr double kPi = 3.141592653589793;           // math.pi
 constexpr double kTwoPi = 2.0 * 3.141592653589793;  // 2*math.pi (exact doubling)
 constexpr double kDegToRad = 3.141592653589793 / 180.0;  // CPython's math.radians multiplier
 constexpr int kVoteThreads = 1024;
+constexpr int kGroupChunk = 256;  // Hough spaces examined per work-stealing ticket
 
 __device__ __forceinline__ int sext8(int v) {
   const int o = v & 0xFF;
@@ -207,6 +208,7 @@ struct VoteArgs {
   uint16_t* creator;         // per grouped position: which of the 16 votes created its bin
   int64_t n_groups;
   int bins;
+  int32_t* ticket;           // work-stealing counter over chunks of kGroupChunk Hough spaces (zeroed per call)
   int32_t* counters;
   int32_t* bin_group;
   int32_t* bin_code;
@@ -235,11 +237,28 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
   const int bins = a.bins;
   const int nb4 = bins * bins * bins * bins;
   const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int s_chunk, s_nlist;
+  __shared__ int s_list[kGroupChunk];
   for (int i = tid; i < nb4; i += kVoteThreads) hist[i] = 0;
   __syncthreads();
-  for (int64_t g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+  // Most (frame, object) spaces are empty: CTAs steal chunks of kGroupChunk spaces, test them in
+  // parallel and only walk the non-empty ones.
+  for (;;) {
+    if (tid == 0) {
+      s_chunk = atomicAdd(a.ticket, 1);
+      s_nlist = 0;
+    }
+    __syncthreads();
+    const int64_t gbase = static_cast<int64_t>(s_chunk) * kGroupChunk;
+    if (gbase >= a.n_groups) break;
+    if (tid < kGroupChunk && gbase + tid < a.n_groups &&
+        a.group_off[gbase + tid + 1] > a.group_off[gbase + tid])
+      s_list[atomicAdd(&s_nlist, 1)] = tid;
+    __syncthreads();
+    const int n_list = s_nlist;
+  for (int li = 0; li < n_list; ++li) {
+    const int64_t g = gbase + s_list[li];
     const int beg = a.group_off[g], end = a.group_off[g + 1];
-    if (beg == end) continue;
     if (tid == 0) s_nbins = s_nvotes = s_rec_cur = s_vote_cur = 0;
     __syncthreads();
     // A: count votes; remember which votes hit an empty counter.
@@ -309,6 +328,8 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
       });
     }
     __syncthreads();
+  }
+    __syncthreads();  // s_list / s_chunk are rewritten by the next ticket
   }
 }
 
@@ -440,7 +461,7 @@ compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict_
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
-  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw;
+  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket;
   uint16_t* creator;
   size_t bytes;
 };
@@ -453,6 +474,7 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
     o += align256(bytes);
     return p;
   };
+  w.ticket = static_cast<int32_t*>(take(256));
   w.group_of = static_cast<int32_t*>(take(m * 4));
   w.group_count = static_cast<int32_t*>(take((groups + 1) * 4));
   w.group_off = static_cast<int32_t*>(take((groups + 1) * 4));
@@ -578,6 +600,7 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
   if (sms <= 0) return SOD_ERR_CUDA;
 
   SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_groups + 1) * 4, st));
+  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 4, st));
   PoseArgs pa;
   pa.sc = *scene;
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = n_matches_dev; pa.n_cap = n_matches;
@@ -597,7 +620,7 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
 
   VoteArgs va;
   va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = out->base_bin; va.creator = w.creator;
-  va.n_groups = n_groups; va.bins = bins; va.counters = out->counters; va.bin_group = out->bin_group;
+  va.n_groups = n_groups; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
   const size_t hist_bytes = static_cast<size_t>(bins) * bins * bins * bins * sizeof(uint32_t);
@@ -607,7 +630,8 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
                                         static_cast<int>(hist_bytes)));
     attr_bytes = hist_bytes;
   }
-  const int64_t vgrid = n_groups < sms ? n_groups : sms;
+  const int64_t n_chunks = (n_groups + kGroupChunk - 1) / kGroupChunk;
+  const int64_t vgrid = n_chunks < sms ? n_chunks : sms;
   hough_vote_kernel<<<static_cast<unsigned>(vgrid), kVoteThreads, hist_bytes, st>>>(va);
   SOD_CHECK_LAUNCH("hough_vote_kernel");
 

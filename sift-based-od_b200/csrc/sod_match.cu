@@ -38,6 +38,9 @@
 #ifndef SOD_EPI_MODE
 #define SOD_EPI_MODE 2
 #endif
+#ifndef SOD_SHARE_THR
+#define SOD_SHARE_THR 0  // (experiment, +3 % on 125k-row shards, -4 % on 1M) the two threads of a query row exchange their 2nd best through shared memory
+#endif
 #ifndef SOD_EXP
 #define SOD_EXP 0  // kernel experiments (timing only, results invalid): 1 = no epilogue math, 2 = no TMEM loads
 #endif
@@ -76,7 +79,9 @@ constexpr int kOffCq = kOffB + kStages * kTileBytes;        // [kCqSlots][128] i
 constexpr int kOffBar = kOffCq + kCqSlots * kCqTileBytes;
 constexpr int kNumBars = 2 * kStages + 12 + kCqSlots;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;         // +1024: manual 1 KB alignment
+constexpr int kOffThr = kOffTmemPtr + 16;                   // [2][kBlockQ] int64: 2nd-best exchange between
+                                                            // the two threads that share a query row
+constexpr int kSmemBytes = kOffThr + 2 * kBlockQ * 8 + 1024;  // +1024: manual 1 KB alignment
 
 struct MatchArgs {
   const int32_t* qn;   // [nq] |q|^2
@@ -140,14 +145,16 @@ constexpr long long kNoKey64 = (static_cast<long long>(kNoKey) << 32) | 0x7FFFFF
 //     running best with the ORIGINAL row index read through the permutation in shared memory,
 //     which settles ties across tiles exactly as cv2 does (lowest original index).
 // All tests are exact; pruning never changes the result.
+// `thr` is the pruning threshold: the row's 2nd best over everything either of its two threads has
+// seen (an element above it cannot be in the merged top-2; ties go through).
 __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __restrict__ cp4,
                                            int cmin, const int32_t* __restrict__ perm_s,
-                                           int idx_base, Top2& best) {
+                                           int idx_base, Top2& best, int& thr) {
 #if SOD_EXP == 1 || SOD_EXP == 2
   return;
 #endif
   const int amax = max_tree32(reinterpret_cast<const int*>(v));
-  if (cmin - 2 * amax > best.d2) return;
+  if (cmin - 2 * amax > thr) return;
   int k[32];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -157,19 +164,32 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
     k[4 * j + 2] = c.z - 512 * static_cast<int>(v[4 * j + 2]);
     k[4 * j + 3] = c.w - 512 * static_cast<int>(v[4 * j + 3]);
   }
-  if ((min_tree32(k) >> 8) > best.d2) return;
+  // group minima of 4 x 8 keys: the update below only touches groups that hold a candidate
+  int g[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    g[i] = imin3(imin3(k[8 * i], k[8 * i + 1], k[8 * i + 2]), imin3(k[8 * i + 3], k[8 * i + 4], k[8 * i + 5]),
+                 min(k[8 * i + 6], k[8 * i + 7]));
+  if ((min(imin3(g[0], g[1], g[2]), g[3]) >> 8) > thr) return;
   int t1 = INT_MAX, t2 = INT_MAX;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int t = max(t1, k[j]);
-    t1 = min(t1, k[j]);
-    t2 = min(t2, t);
+  for (int i = 0; i < 4; ++i) {
+    if ((g[i] >> 8) <= thr) {
+#pragma unroll
+      for (int j = 8 * i; j < 8 * i + 8; ++j) {
+        const int t = max(t1, k[j]);
+        t1 = min(t1, k[j]);
+        t2 = min(t2, t);
+      }
+    }
   }
   const int o1 = perm_s[t1 & 0xFF];
   if (o1 >= 0) best.offer(t1 >> 8, idx_base + o1);
-  if ((t2 >> 8) <= best.d2) {
+  thr = min(thr, best.d2);
+  if ((t2 >> 8) <= thr) {
     const int o2 = perm_s[t2 & 0xFF];
     if (o2 >= 0) best.offer(t2 >> 8, idx_base + o2);
+    thr = min(thr, best.d2);
   }
 }
 
@@ -219,6 +239,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 2 * kBlockQ; i += kThreads)  // threshold exchange slots: tag 0 = unused
+    reinterpret_cast<long long*>(smem + kOffThr)[i] = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -307,14 +329,26 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int h = (e >> 2) & 1;         // which query half-tile
     const uint32_t par = e >> 3;        // which 64-column half of every tile
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    uint32_t step = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    uint32_t step = 0, ucount = 1;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
       const int seg = u / a.n_qblocks;
       const int qb = u - seg * a.n_qblocks;
       const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
       const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
       Top2 best{kNoKey64, kNoKey64, kNoKey};
+#if SOD_EPI_MODE != 1 && SOD_SHARE_THR
+      // The row's other thread (other tile parity / column half) publishes its 2nd best here, tagged
+      // with the unit counter so a value from another unit (= another query row) is never used.
+      // 8-byte shared-memory accesses are single instructions; a stale value only prunes less.
+      volatile long long* thr_mine =
+          reinterpret_cast<volatile long long*>(smem + kOffThr) + par * kBlockQ + (row - qb * kBlockQ);
+      volatile long long* thr_other =
+          reinterpret_cast<volatile long long*>(smem + kOffThr) + (par ^ 1u) * kBlockQ + (row - qb * kBlockQ);
+      const long long tag = static_cast<long long>(ucount) << 32;
+      int published = kNoKey;
+#endif
+      int thr = kNoKey;
       for (int t = t0; t < t1; ++t, ++step) {
 #if SOD_EPI_MODE == 2
         if ((step & 1u) != par) continue;
@@ -326,6 +360,12 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         const int32_t* cs = reinterpret_cast<const int32_t*>(smem + kOffCq + slot * kCqTileBytes);
         const int32_t* perm_s = cs + kCqPerm;
+#if SOD_EPI_MODE != 1 && SOD_SHARE_THR
+        {
+          const long long o = *thr_other;
+          if ((o >> 32) == (tag >> 32)) thr = min(thr, static_cast<int>(o));
+        }
+#endif
 #if SOD_EPI_MODE == 1
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
         const int4* c4 = reinterpret_cast<const int4*>(cs);
@@ -337,10 +377,10 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(acc, h));
-        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
-        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
-        top2_chunk(v + 2 * kChunk, c4 + 16, cmin.z, perm_s, a.idx_base, best);
-        top2_chunk(v + 3 * kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best);
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
+        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
+        top2_chunk(v + 2 * kChunk, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
+        top2_chunk(v + 3 * kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
 #elif SOD_EPI_MODE == 2
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
         const int4* c4 = reinterpret_cast<const int4*>(cs);
@@ -349,16 +389,16 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #if SOD_EXP != 2
         tmem_ld64_wait(taddr, v);
 #endif
-        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
-        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
+        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
 #if SOD_EXP != 2
         tmem_ld64_wait(taddr + 2 * kChunk, v);
 #endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(acc, h));
-        top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best);
-        top2_chunk(v + kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best);
+        top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
+        top2_chunk(v + kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
 #else
         const uint32_t taddr =
             tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN + par * (2 * kChunk);
@@ -371,8 +411,14 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (lane == 0) mbar_arrive(bar_tempty(acc, h));
         const int4* c4 = reinterpret_cast<const int4*>(cs) + par * 16;
         const int2 cmin = *reinterpret_cast<const int2*>(cs + kTileN + par * 2);
-        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best);
-        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best);
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
+        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
+#endif
+#if SOD_EPI_MODE != 1 && SOD_SHARE_THR
+        if (best.d2 < published) {
+          published = best.d2;
+          *thr_mine = tag | static_cast<unsigned>(published);
+        }
 #endif
       }
       if (row < a.nq) {
