@@ -43,7 +43,16 @@ class ModelDatabase:
 class DetectionPipeline:
     def __init__(self, db: ModelDatabase, max_queries: int, frame_wh: np.ndarray, rank: int = 0,
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
-                 affine_threshold: int = 4, per_object_spaces: bool = True, device: str | torch.device = "cuda"):
+                 affine_threshold: int = 4, per_object_spaces: bool = True, device: str | torch.device = "cuda",
+                 shard: str = "db"):
+        """shard="db": database rows split over the ranks, one all-gather of top-2.
+        shard="frames": database replicated on every rank, the caller gives each rank its own frames
+        (no collective at all); the pipeline then behaves exactly like a single-GPU one."""
+        if shard not in ("db", "frames"):
+            raise ValueError("shard must be 'db' or 'frames'")
+        self.shard_mode = shard
+        if shard == "frames":
+            rank, world = 0, 1
         self.rank, self.world, self.group = rank, world, group
         self.device = torch.device(device)
         self.bins, self.vote_threshold, self.affine_threshold = bins, vote_threshold, affine_threshold
