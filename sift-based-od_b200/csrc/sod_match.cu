@@ -35,6 +35,7 @@
 //   1 = 8 warps: (lane quadrant x query half), 128 columns per tile, slot released right after the load
 //   2 = 16 warps: as 1 but split by tile parity (every other tile each), two 64-column loads
 //   3 = 16 warps: split by column half (64 columns of every tile each)
+//   4 = 24 warps: 3-way tile interleave (every third tile each), four 32-column loads
 #ifndef SOD_EPI_MODE
 #define SOD_EPI_MODE 2
 #endif
@@ -54,19 +55,20 @@ constexpr int kBlockQ = kTileM * kHalves;   // 256 query rows per unit
 constexpr int kTileN = SOD_TILE_ROWS;       // database rows per MMA
 constexpr int kTileBytes = kTileN * SOD_DESC_DIM;  // 16 KB (A half-tile has the same size)
 constexpr int kStages = 6;
-constexpr int kCqSlots = kStages + 4;       // see the slot-reuse argument in the producer
+constexpr int kCqSlots = kStages + 6;       // see the slot-reuse argument in the producer (12 covers
+                                            // up to a 3-way tile interleave of the epilogue warps)
 constexpr int kChunk = 32;                  // accumulator columns per tcgen05.ld
 constexpr int kCqTile = SOD_CQ_TILE_INTS;   // 128 x |t|^2 + 4 per-chunk minima + 128 x original row
 constexpr int kCqPerm = kTileN + 4;         // offset of the permutation inside a tile's slice
 constexpr int kCqTileBytes = kCqTile * 4;   // 1040 B, a multiple of 16 for the bulk copy
 constexpr int kNoKey = 0x7FFFFF;            // |t|^2 of padding rows / "no candidate yet" (> 128*255^2,
                                             // and (kNoKey << 8 | 127) still fits int32)
-constexpr int kParity = SOD_EPI_MODE == 1 ? 1 : 2;  // candidate lists per row and segment
+constexpr int kParity = SOD_EPI_MODE == 1 ? 1 : SOD_EPI_MODE == 4 ? 3 : 2;  // candidate lists per row and segment
 constexpr int kEpiWarps = 4 * kHalves * kParity;    // (TMEM lane quadrant) x (query half) x (split)
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kRegsLight = 56;      // producer / MMA / allocator warpgroup after setmaxnreg.dec
-constexpr int kRegsEpilogue = SOD_EPI_MODE == 1 ? 224 : 104;  // accumulator registers + 32 keys + state
+constexpr int kRegsEpilogue = SOD_EPI_MODE == 1 ? 224 : SOD_EPI_MODE == 4 ? 72 : 104;  // accumulators + keys + state
 // setmaxnreg only moves registers inside the CTA's launch allocation (threads x launch registers,
 // the latter a multiple of 8): asking for more makes setmaxnreg.inc wait forever.
 constexpr int kRegsLaunch = 65536 / kThreads / 8 * 8;
@@ -77,7 +79,11 @@ constexpr int kOffA = 0;                                    // [2 buffers][2 hal
 constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;     // [kStages][16 KB]
 constexpr int kOffCq = kOffB + kStages * kTileBytes;        // [kCqSlots][128] int32
 constexpr int kOffBar = kOffCq + kCqSlots * kCqTileBytes;
-constexpr int kNumBars = 2 * kStages + 12 + kCqSlots;
+constexpr int kBarGroups = SOD_EPI_MODE == 4 ? 3 : 2;  // accumulator barriers are indexed by step % kBarGroups:
+                                                       // every barrier is then waited on by ONE set of epilogue
+                                                       // warps for consecutive phases (a parity wait must never
+                                                       // skip a phase)
+constexpr int kNumBars = 2 * kStages + 4 + 4 * kBarGroups + kCqSlots;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kOffThr = kOffTmemPtr + 16;                   // [2][kBlockQ] int64: 2nd-best exchange between
                                                             // the two threads that share a query row
@@ -209,10 +215,10 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto bar_afull = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
   auto bar_aempty = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
-  // accumulator slots are tracked per (buffer, half): four independent 128-column slots
-  auto bar_tfull = [&](int b, int h) { return bar0 + 8u * (2 * kStages + 4 + 2 * b + h); };
-  auto bar_tempty = [&](int b, int h) { return bar0 + 8u * (2 * kStages + 8 + 2 * b + h); };
-  auto bar_cqfull = [&](int s) { return bar0 + 8u * (2 * kStages + 12 + s); };
+  // accumulator hand-off barriers per (step % kBarGroups, half); the TMEM slot itself is step & 1
+  auto bar_tfull = [&](int g, int h) { return bar0 + 8u * (2 * kStages + 4 + 2 * g + h); };
+  auto bar_tempty = [&](int g, int h) { return bar0 + 8u * (2 * kStages + 4 + 2 * kBarGroups + 2 * g + h); };
+  auto bar_cqfull = [&](int s) { return bar0 + 8u * (2 * kStages + 4 + 4 * kBarGroups + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
   if (warp == 0 && lane == 0) {
@@ -227,11 +233,12 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_afull(b), 1);
       mbar_init(bar_aempty(b), kHalves);
-      for (int h = 0; h < kHalves; ++h) {
-        mbar_init(bar_tfull(b, h), 1);
-        mbar_init(bar_tempty(b, h), SOD_EPI_MODE == 3 ? 8 : 4);  // warps that read one slot
-      }
     }
+    for (int g = 0; g < kBarGroups; ++g)
+      for (int h = 0; h < kHalves; ++h) {
+        mbar_init(bar_tfull(g, h), 1);
+        mbar_init(bar_tempty(g, h), SOD_EPI_MODE == 3 ? 8 : 4);  // warps that read one slot
+      }
     for (int s = 0; s < kCqSlots; ++s) mbar_init(bar_cqfull(s), 1);
     fence_mbar_init();
   }
@@ -249,7 +256,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int total_units = a.n_qblocks * a.n_seg;
 
   if (warp < 4) {
-    setmaxnreg_dec<kRegsLight>();  // this warpgroup hands its registers to the epilogue warpgroups
+    if constexpr (kRegsLight < kRegsLaunch)
+      setmaxnreg_dec<kRegsLight>();  // this warpgroup hands its registers to the epilogue warpgroups
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -302,17 +310,18 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const uint64_t adesc = umma_desc_k128(base + kOffA + (ab * kHalves + h) * kTileBytes);
       for (int t = t0; t < t1; ++t, ++step) {
         const uint32_t s = step % kStages, ph = (step / kStages) & 1u;
-        const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
+        const uint32_t acc = step & 1u;
         const uint64_t bdesc = umma_desc_k128(base + kOffB + s * kTileBytes);
         const uint32_t d = tmem_base + acc * (kHalves * kTileN) + h * kTileN;
         mbar_wait(bar_full(s), ph);
-        mbar_wait(bar_tempty(acc, h), accph ^ 1u);
+        if (step >= 2)  // slot step & 1 was last used by step - 2: wait for its epilogue warps' release
+          mbar_wait(bar_tempty((step - 2) % kBarGroups, h), ((step - 2) / kBarGroups) & 1u);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < SOD_DESC_DIM / 32; ++k)  // K = 32 bytes per UTCIMMA: +2 x 16 B
             umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          umma_commit(bar_tfull(acc, h));  // this half is ready for its epilogue warps
+          umma_commit(bar_tfull(step % kBarGroups, h));  // this half is ready for its epilogue warps
           umma_commit(bar_empty(s));       // (count 2) database stage free once both halves retire
         }
         __syncwarp();
@@ -323,11 +332,11 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   } else {
     // ------------------------------------------------------------------ epilogue
-    setmaxnreg_inc<kRegsEpilogue>();
+    if constexpr (kRegsEpilogue > kRegsLaunch) setmaxnreg_inc<kRegsEpilogue>();
     const int e = warp - 4;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int h = (e >> 2) & 1;         // which query half-tile
-    const uint32_t par = e >> 3;        // which 64-column half of every tile
+    const uint32_t par = e >> 3;        // which tiles (modes 2, 4) or which 64-column half (mode 3)
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t step = 0, ucount = 1;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
@@ -352,11 +361,13 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int t = t0; t < t1; ++t, ++step) {
 #if SOD_EPI_MODE == 2
         if ((step & 1u) != par) continue;
+#elif SOD_EPI_MODE == 4
+        if (step % 3u != par) continue;
 #endif
-        const uint32_t acc = step & 1u, accph = (step >> 1) & 1u;
+        const uint32_t acc = step & 1u, bg = step % kBarGroups, bgph = (step / kBarGroups) & 1u;
         const uint32_t slot = step % kCqSlots, cqph = (step / kCqSlots) & 1u;
         mbar_wait(bar_cqfull(slot), cqph);  // landed long ago: returns at the first poll
-        mbar_wait(bar_tfull(acc, h), accph);
+        mbar_wait(bar_tfull(bg, h), bgph);
         tc_fence_after();
         const int32_t* cs = reinterpret_cast<const int32_t*>(smem + kOffCq + slot * kCqTileBytes);
         const int32_t* perm_s = cs + kCqPerm;
@@ -376,7 +387,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #endif
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(acc, h));
+        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
         top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
         top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
         top2_chunk(v + 2 * kChunk, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
@@ -396,9 +407,25 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #endif
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(acc, h));
+        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
         top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
         top2_chunk(v + kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
+#elif SOD_EPI_MODE == 4
+        const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
+        const int4* c4 = reinterpret_cast<const int4*>(cs);
+        const int4 cmin = c4[kTileN / 4];
+        uint32_t v[kChunk];
+        tmem_ld32_wait(taddr, v);
+        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
+        tmem_ld32_wait(taddr + kChunk, v);
+        top2_chunk(v, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
+        tmem_ld32_wait(taddr + 2 * kChunk, v);
+        top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
+        tmem_ld32_wait(taddr + 3 * kChunk, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
+        top2_chunk(v, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
 #else
         const uint32_t taddr =
             tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN + par * (2 * kChunk);
@@ -408,7 +435,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #endif
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(acc, h));
+        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
         const int4* c4 = reinterpret_cast<const int4*>(cs) + par * 16;
         const int2 cmin = *reinterpret_cast<const int2*>(cs + kTileN + par * 2);
         top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
