@@ -175,11 +175,15 @@ size_t sod_hough_workspace_bytes(int64_t n_matches, int64_t n_groups);
  * (PoseBin.py:19-54): every match votes into the <=16 bins (ix+w, iy+x, itheta+y, isigma+z) whose
  * coordinates are all < bins.  n_matches is the capacity of match_q/match_t; if n_matches_dev is
  * not NULL the actual count is read from it on the device.  sigma_lut[k - SOD_SIGMA_LUT_MIN] is
- * the isigma of scale factor 2^k (device int32[SOD_SIGMA_LUT_LEN]). */
+ * the isigma of scale factor 2^k (device int32[SOD_SIGMA_LUT_LEN]).  Every non-empty bin gets a
+ * record (group, code, count, offset); bins with at least detail_min_count votes also get their
+ * member list sorted, the running means and the insertion-order key (1 = all bins, as the
+ * reference's dict; a caller that only goes on to sod_affine_verify passes its vote threshold and
+ * skips that work for the bins it will never look at). */
 int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
                    int64_t n_matches, const int32_t* n_matches_dev, int32_t bins,
-                   const int32_t* sigma_lut, const sod_hough_out* out, void* workspace,
-                   size_t workspace_bytes, sod_stream_t stream);
+                   const int32_t* sigma_lut, int32_t detail_min_count, const sod_hough_out* out,
+                   void* workspace, size_t workspace_bytes, sod_stream_t stream);
 
 /* Outputs of sod_affine_verify (device), one entry per bin that entered with >= vote_threshold. */
 typedef struct {

@@ -81,6 +81,98 @@ __device__ void jacobi3(double (&A)[3][3], double (&V)[3][3]) {
   }
 }
 
+// pinv(S) applied to the two right-hand sides: S = [[sxx,sxy,sx],[sxy,syy,sy],[sx,sy,n]].
+// Returns 1 if S is numerically singular (smallest |eigenvalue| <= 1e-10 x largest).
+__device__ __forceinline__ int solve_affine(double sxx, double sxy, double sx, double syy, double sy,
+                                            double sn, const double (&ru)[3], const double (&rv)[3],
+                                            double (&pu)[3], double (&pv)[3]) {
+  double A[3][3] = {{sxx, sxy, sx}, {sxy, syy, sy}, {sx, sy, sn}};
+  double V[3][3];
+  jacobi3(A, V);
+  const double wv[3] = {A[0][0], A[1][1], A[2][2]};
+  const double wmax = fmax(fabs(wv[0]), fmax(fabs(wv[1]), fabs(wv[2])));
+  const double wmin = fmin(fabs(wv[0]), fmin(fabs(wv[1]), fabs(wv[2])));
+  const double cut = 1e-15 * wmax;  // numpy.linalg.pinv default rcond
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pu[i] = pv[i] = 0.0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    if (!(fabs(wv[e]) > cut)) continue;
+    const double du = (V[0][e] * ru[0] + V[1][e] * ru[1] + V[2][e] * ru[2]) / wv[e];
+    const double dv = (V[0][e] * rv[0] + V[1][e] * rv[1] + V[2][e] * rv[2]) / wv[e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      pu[i] += V[i][e] * du;
+      pv[i] += V[i][e] * dv;
+    }
+  }
+  return wmin <= 1e-10 * wmax ? 1 : 0;
+}
+
+constexpr int kSmallAffine = 32;  // bins up to this size are verified by a single thread
+
+// One THREAD per small valid bin (the vast majority: random bins with 5-10 votes): the alive set is
+// a 32-bit mask, every pass re-gathers the coordinates of the alive pairs.
+__global__ void affine_verify_small_kernel(const AffineArgs a) {
+  int64_t n_valid = a.out.counters[0];
+  if (n_valid > a.out.cap_valid) n_valid = a.out.cap_valid;
+  const float2* mxy = reinterpret_cast<const float2*>(a.sc.model.xy);
+  const float2* qxy = reinterpret_cast<const float2*>(a.sc.query.xy);
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < n_valid;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int rec = a.out.valid_bin[v];
+    const int cnt = a.bin_count[rec];
+    if (cnt > kSmallAffine) continue;
+    const int off = a.bin_offset[rec];
+    const int frame = a.bin_group[rec] / a.sc.groups_per_frame;
+    const int isigma = a.bin_code[rec] % a.bins;
+    const double x_ref = a.factor_x > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame] * isigma), a.factor_x) : inf;
+    const double y_ref = a.factor_y > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor_y) : inf;
+    const int32_t* mem = a.members + off;
+    unsigned alive = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    int n_alive = cnt, passes = 0, live = 0, singular = 0;
+    double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
+    while (true) {
+      double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0, sn = 0;
+      double ru[3] = {0, 0, 0}, rv[3] = {0, 0, 0};
+      for (int j = 0; j < cnt; ++j) {
+        if (!(alive >> j & 1u)) continue;
+        const int m = mem[j];
+        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+        const double x = pm.x, y = pm.y, u = pq.x, w = pq.y;
+        sxx += x * x; sxy += x * y; sx += x; syy += y * y; sy += y; sn += 1.0;
+        ru[0] += x * u; ru[1] += y * u; ru[2] += u; rv[0] += x * w; rv[1] += y * w; rv[2] += w;
+      }
+      singular |= solve_affine(sxx, sxy, sx, syy, sy, sn, ru, rv, pu, pv);
+      int removed = 0;
+      for (int j = 0; j < cnt; ++j) {
+        if (!(alive >> j & 1u)) continue;
+        const int m = mem[j];
+        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+        const double x = pm.x, y = pm.y;
+        const double ua = __dadd_rn(__dadd_rn(__dmul_rn(pu[0], x), __dmul_rn(pu[1], y)), pu[2]);
+        const double va = __dadd_rn(__dadd_rn(__dmul_rn(pv[0], x), __dmul_rn(pv[1], y)), pv[2]);
+        if (fabs(ua - static_cast<double>(pq.x)) > x_ref || fabs(va - static_cast<double>(pq.y)) > y_ref) {
+          alive &= ~(1u << j);
+          ++removed;
+        }
+      }
+      n_alive -= removed;
+      ++passes;
+      if (n_alive < a.affine_threshold) break;
+      if (removed == 0) { live = 1; break; }
+      if (a.max_passes > 0 && passes >= a.max_passes) { live = 1; break; }
+    }
+    uint8_t* keep = a.out.member_keep + off;
+    for (int j = 0; j < cnt; ++j) keep[j] = (alive >> j) & 1u;
+    double* p = a.out.params + v * 6;
+    p[0] = pu[0]; p[1] = pu[1]; p[2] = pv[0]; p[3] = pv[1]; p[4] = pu[2]; p[5] = pv[2];
+    a.out.votes[v] = n_alive;
+    a.out.status[v] = live | (singular << 1) | (passes << 8);
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -98,6 +190,7 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
   for (int64_t v = warp; v < n_valid; v += n_warps) {
     const int rec = a.out.valid_bin[v];
     const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
+    if (cnt <= kSmallAffine) continue;  // handled by affine_verify_small_kernel
     const int frame = a.bin_group[rec] / a.sc.groups_per_frame;
     const int isigma = a.bin_code[rec] % a.bins;
     // remove_outliers thresholds use pose[3], the sigma BIN INDEX (AffineParameters.py:120-121)
@@ -124,29 +217,8 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
       sxx = warp_sum(sxx); sxy = warp_sum(sxy); sx = warp_sum(sx); syy = warp_sum(syy);
       sy = warp_sum(sy); sn = warp_sum(sn); sxu = warp_sum(sxu); syu = warp_sum(syu);
       su = warp_sum(su); sxv = warp_sum(sxv); syv = warp_sum(syv); sv = warp_sum(sv);
-      double A[3][3] = {{sxx, sxy, sx}, {sxy, syy, sy}, {sx, sy, sn}};
-      double V[3][3];
-      jacobi3(A, V);
-      const double w0 = A[0][0], w1 = A[1][1], w2 = A[2][2];
-      const double wmax = fmax(fabs(w0), fmax(fabs(w1), fabs(w2)));
-      const double wmin = fmin(fabs(w0), fmin(fabs(w1), fabs(w2)));
-      const double cut = 1e-15 * wmax;  // numpy.linalg.pinv default rcond
-      if (wmin <= 1e-10 * wmax) singular = 1;
       const double ru[3] = {sxu, syu, su}, rv[3] = {sxv, syv, sv};
-      const double wv[3] = {w0, w1, w2};
-#pragma unroll
-      for (int i = 0; i < 3; ++i) pu[i] = pv[i] = 0.0;
-#pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        if (!(fabs(wv[e]) > cut)) continue;
-        const double du = (V[0][e] * ru[0] + V[1][e] * ru[1] + V[2][e] * ru[2]) / wv[e];
-        const double dv = (V[0][e] * rv[0] + V[1][e] * rv[1] + V[2][e] * rv[2]) / wv[e];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          pu[i] += V[i][e] * du;
-          pv[i] += V[i][e] * dv;
-        }
-      }
+      singular |= solve_affine(sxx, sxy, sx, syy, sy, sn, ru, rv, pu, pv);
       int removed = 0;
       for (int j = lane; j < cnt; j += 32) {
         if (!keep[j]) continue;
@@ -235,6 +307,8 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
   a.factor_x = factor_x; a.factor_y = factor_y; a.max_passes = max_passes; a.out = *out;
   affine_select_kernel<<<sms * 4, 256, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_select_kernel");
+  affine_verify_small_kernel<<<sms * 8, 128, 0, st>>>(a);
+  SOD_CHECK_LAUNCH("affine_verify_small_kernel");
   affine_verify_kernel<<<sms * 8, 128, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_verify_kernel");
   return SOD_OK;

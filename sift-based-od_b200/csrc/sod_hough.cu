@@ -26,7 +26,7 @@ constexpr double kPi = 3.141592653589793;           // math.pi
 constexpr double kTwoPi = 2.0 * 3.141592653589793;  // 2*math.pi (exact doubling)
 constexpr double kDegToRad = 3.141592653589793 / 180.0;  // CPython's math.radians multiplier
 constexpr int kVoteThreads = 1024;
-constexpr int kGroupChunk = 256;  // Hough spaces examined per work-stealing ticket
+constexpr int kGroupChunk = 256;  // most Hough spaces examined per work-stealing ticket
 
 __device__ __forceinline__ int sext8(int v) {
   const int o = v & 0xFF;
@@ -208,7 +208,8 @@ struct VoteArgs {
   uint16_t* creator;         // per grouped position: which of the 16 votes created its bin
   int64_t n_groups;
   int bins;
-  int32_t* ticket;           // work-stealing counter over chunks of kGroupChunk Hough spaces (zeroed per call)
+  int group_chunk;           // Hough spaces per ticket: 1 for few large spaces ... kGroupChunk for many sparse ones
+  int32_t* ticket;           // work-stealing counter over chunks of group_chunk Hough spaces (zeroed per call)
   int32_t* counters;
   int32_t* bin_group;
   int32_t* bin_code;
@@ -249,9 +250,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
       s_nlist = 0;
     }
     __syncthreads();
-    const int64_t gbase = static_cast<int64_t>(s_chunk) * kGroupChunk;
+    const int64_t gbase = static_cast<int64_t>(s_chunk) * a.group_chunk;
     if (gbase >= a.n_groups) break;
-    if (tid < kGroupChunk && gbase + tid < a.n_groups &&
+    if (tid < a.group_chunk && gbase + tid < a.n_groups &&
         a.group_off[gbase + tid + 1] > a.group_off[gbase + tid])
       s_list[atomicAdd(&s_nlist, 1)] = tid;
     __syncthreads();
@@ -348,17 +349,92 @@ struct FinishArgs {
   double* bin_mean;
   int64_t cap_bins;
   int bins;
+  int detail_min_count;  // bins with fewer votes get no sorted members / means / order key
+  int32_t* big_list;     // bins too large for one thread, finished by hough_finish_big_kernel
+  int32_t* big_count;
+  int64_t big_cap;
 };
 
-// One warp per bin: rank-sort the members (ids are distinct), then lanes 0..5 each run one of the
-// six sequential running means of PoseBin.update_posebin: (old * votes + new) / (votes + 1).
+constexpr int kSmallBin = 16;  // bins up to this size are finished by a single thread
+
+__device__ __forceinline__ int64_t order_key(const FinishArgs& a, int64_t rec, int first) {
+  const uint32_t base = a.base_bin[first];
+  int code = a.bin_code[rec];
+  const int b = a.bins;
+  const int cs = code % b; code /= b;
+  const int ct = code % b; code /= b;
+  const int cy = code % b; code /= b;
+  const int cx = code;
+  const int o = ((cx - static_cast<int>(base & 0xFF)) << 3) | ((cy - static_cast<int>((base >> 8) & 0xFF)) << 2) |
+                ((ct - static_cast<int>((base >> 16) & 0xFF)) << 1) | (cs - static_cast<int>(base >> 24));
+  return static_cast<int64_t>(first) * 16 + o;
+}
+
+__device__ __forceinline__ double mean_component(const FinishArgs& a, int m, int comp) {
+  if (comp < 4) return a.pose[static_cast<int64_t>(m) * 4 + comp];
+  return a.sc.image_size[2 * a.sc.model_image[a.match_t[m]] + (comp - 4)];
+}
+
+// One THREAD per bin (almost all bins hold a handful of votes): sort the members by match id (the
+// reference's append order), run the six sequential running means of PoseBin.update_posebin,
+// (old * votes + new) / (votes + 1), and compute the insertion-order key.  Larger bins are queued
+// for the warp-per-bin kernel.
 __global__ void hough_finish_kernel(const FinishArgs a) {
+  int64_t n_bins = a.counters[0];
+  if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
+  for (int64_t rec = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; rec < n_bins;
+       rec += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cnt = a.bin_count[rec];
+    if (cnt < a.detail_min_count) continue;
+    if (cnt > kSmallBin) {
+      const int slot = atomicAdd(a.big_count, 1);
+      if (slot < a.big_cap) a.big_list[slot] = static_cast<int32_t>(rec);
+      continue;
+    }
+    const int off = a.bin_offset[rec];
+    int m[kSmallBin];
+#pragma unroll
+    for (int i = 0; i < kSmallBin; ++i) m[i] = i < cnt ? a.members_raw[off + i] : INT_MAX;
+#pragma unroll
+    for (int i = 1; i < kSmallBin; ++i) {  // insertion sort, fully unrolled: stays in registers
+#pragma unroll
+      for (int j = i; j > 0; --j) {
+        const int lo = min(m[j - 1], m[j]), hi = max(m[j - 1], m[j]);
+        m[j - 1] = lo;
+        m[j] = hi;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kSmallBin; ++i)
+      if (i < cnt) a.members[off + i] = m[i];
+#pragma unroll
+    for (int comp = 0; comp < 6; ++comp) {
+      double mean = 0.0;
+#pragma unroll
+      for (int j = 0; j < kSmallBin; ++j) {
+        if (j < cnt) {
+          const double v = mean_component(a, m[j], comp);
+          mean = j == 0 ? v
+                        : __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v),
+                                    static_cast<double>(j + 1));
+        }
+      }
+      a.bin_mean[rec * 6 + comp] = mean;
+    }
+    a.bin_order[rec] = order_key(a, rec, m[0]);
+  }
+}
+
+// One warp per large bin: rank-sort the members (ids are distinct), then lanes 0..5 each run one
+// of the six sequential running means.
+__global__ void hough_finish_big_kernel(const FinishArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  int64_t n_bins = a.counters[0];
-  if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
-  for (int64_t rec = warp; rec < n_bins; rec += n_warps) {
+  int64_t n_big = *a.big_count;
+  if (n_big > a.big_cap) n_big = a.big_cap;
+  for (int64_t b = warp; b < n_big; b += n_warps) {
+    const int64_t rec = a.big_list[b];
     const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
     const int32_t* raw = a.members_raw + off;
     int32_t* out = a.members + off;
@@ -372,35 +448,14 @@ __global__ void hough_finish_kernel(const FinishArgs a) {
     if (lane < 6) {
       double mean = 0.0;
       for (int j = 0; j < cnt; ++j) {
-        const int m = out[j];
-        double v;
-        if (lane < 4) {
-          v = a.pose[static_cast<int64_t>(m) * 4 + lane];
-        } else {
-          const int img = a.sc.model_image[a.match_t[m]];
-          v = a.sc.image_size[2 * img + (lane - 4)];
-        }
+        const double v = mean_component(a, out[j], lane);
         mean = j == 0 ? v
                       : __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v),
                                   static_cast<double>(j + 1));
       }
       a.bin_mean[rec * 6 + lane] = mean;
     }
-    if (lane == 0) {
-      const int first = out[0];
-      const uint32_t base = a.base_bin[first];
-      int code = a.bin_code[rec];
-      const int b = a.bins;
-      const int cs = code % b; code /= b;
-      const int ct = code % b; code /= b;
-      const int cy = code % b; code /= b;
-      const int cx = code;
-      const int o = ((cx - static_cast<int>(base & 0xFF)) << 3) |
-                    ((cy - static_cast<int>((base >> 8) & 0xFF)) << 2) |
-                    ((ct - static_cast<int>((base >> 16) & 0xFF)) << 1) |
-                    (cs - static_cast<int>(base >> 24));
-      a.bin_order[rec] = static_cast<int64_t>(first) * 16 + o;
-    }
+    if (lane == 0) a.bin_order[rec] = order_key(a, rec, out[0]);
   }
 }
 
@@ -461,7 +516,8 @@ compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict_
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
-  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket;
+  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket, *big_list;
+  int64_t big_cap;
   uint16_t* creator;
   size_t bytes;
 };
@@ -482,6 +538,8 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.grouped = static_cast<int32_t*>(take(m * 4));
   w.creator = static_cast<uint16_t*>(take(m * 2));
   w.members_raw = static_cast<int32_t*>(take(cap_votes * 4));
+  w.big_cap = cap_votes / (kSmallBin + 1) + 1;
+  w.big_list = static_cast<int32_t*>(take(w.big_cap * 4));
   w.bytes = o;
   return w;
 }
@@ -567,8 +625,8 @@ size_t sod_hough_workspace_bytes(int64_t n_matches, int64_t n_groups) {
 
 int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
                    int64_t n_matches, const int32_t* n_matches_dev, int32_t bins,
-                   const int32_t* sigma_lut, const sod_hough_out* out, void* workspace,
-                   size_t workspace_bytes, sod_stream_t stream) {
+                   const int32_t* sigma_lut, int32_t detail_min_count, const sod_hough_out* out,
+                   void* workspace, size_t workspace_bytes, sod_stream_t stream) {
   SOD_CHECK_ARG(scene && out, "null scene/out");
   SOD_CHECK_ARG(n_matches >= 0 && n_matches < (int64_t(1) << 27), "n_matches out of range");
   SOD_CHECK_ARG(bins >= 1, "bins < 1");
@@ -600,7 +658,7 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
   if (sms <= 0) return SOD_ERR_CUDA;
 
   SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_groups + 1) * 4, st));
-  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 4, st));
+  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 8, st));  // [0] vote ticket, [1] big-bin count
   PoseArgs pa;
   pa.sc = *scene;
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = n_matches_dev; pa.n_cap = n_matches;
@@ -630,7 +688,10 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
                                         static_cast<int>(hist_bytes)));
     attr_bytes = hist_bytes;
   }
-  const int64_t n_chunks = (n_groups + kGroupChunk - 1) / kGroupChunk;
+  int64_t group_chunk = n_groups / (static_cast<int64_t>(sms) * 8);
+  group_chunk = group_chunk < 1 ? 1 : (group_chunk > kGroupChunk ? kGroupChunk : group_chunk);
+  va.group_chunk = static_cast<int>(group_chunk);
+  const int64_t n_chunks = (n_groups + group_chunk - 1) / group_chunk;
   const int64_t vgrid = n_chunks < sms ? n_chunks : sms;
   hough_vote_kernel<<<static_cast<unsigned>(vgrid), kVoteThreads, hist_bytes, st>>>(va);
   SOD_CHECK_LAUNCH("hough_vote_kernel");
@@ -641,8 +702,12 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
   fa.bin_code = out->bin_code; fa.bin_count = out->bin_count; fa.bin_offset = out->bin_offset;
   fa.members_raw = w.members_raw; fa.members = out->members; fa.bin_order = out->bin_order;
   fa.bin_mean = out->bin_mean; fa.cap_bins = out->cap_bins; fa.bins = bins;
+  fa.detail_min_count = detail_min_count; fa.big_list = w.big_list; fa.big_count = w.ticket + 1;
+  fa.big_cap = w.big_cap;
   hough_finish_kernel<<<sms * 8, 256, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_kernel");
+  hough_finish_big_kernel<<<sms * 8, 256, 0, st>>>(fa);
+  SOD_CHECK_LAUNCH("hough_finish_big_kernel");
   return SOD_OK;
 }
 

@@ -281,7 +281,10 @@ class HoughVoter:
         self._ws = None
         self._res: HoughResult | None = None
 
-    def vote(self, match_q: torch.Tensor, match_t: torch.Tensor, n_dev: torch.Tensor | None = None) -> HoughResult:
+    def vote(self, match_q: torch.Tensor, match_t: torch.Tensor, n_dev: torch.Tensor | None = None,
+             detail_min_count: int = 1) -> HoughResult:
+        """detail_min_count: bins with fewer votes get a record and a count but no sorted members,
+        means or order key (pass the vote threshold when only verified bins matter)."""
         match_q = _require_cuda(match_q, torch.int32, "match_q")
         match_t = _require_cuda(match_t, torch.int32, "match_t")
         m = int(match_q.shape[0])
@@ -294,7 +297,8 @@ class HoughVoter:
         res = self._res
         s, o = sc.struct(), res.struct()
         check(lib.sod_hough_vote(C.byref(s), _ptr(match_q), _ptr(match_t), m, _ptr(n_dev), self.bins,
-                                 _ptr(self.lut), C.byref(o), _ptr(self._ws), self._ws.numel(), _stream()),
+                                 _ptr(self.lut), int(detail_min_count), C.byref(o), _ptr(self._ws),
+                                 self._ws.numel(), _stream()),
               "sod_hough_vote")
         return res
 

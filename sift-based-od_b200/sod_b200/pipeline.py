@@ -82,7 +82,7 @@ class DetectionPipeline:
         if world > 1:
             self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
             self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
-        self.launches_per_call = 14  # our kernels per detect_device call
+        self.launches_per_call = 16  # our kernels per detect_device call
 
     # ---------------------------------------------------------------- device-resident inputs
     def load_queries(self, des, xy, angle, octave, frame) -> int:
@@ -118,7 +118,7 @@ class DetectionPipeline:
             idx, d2, dist_f, ok = E.merge_top2(idx[None], d2[None])
         lo, hi = (self.row_lo, self.row_hi) if self.world > 1 else (0, 2 ** 31 - 1)
         mq, mt, n_dev = E.compact_matches(idx, ok, lo, hi)
-        hough = self.voter.vote(mq, mt, n_dev)
+        hough = self.voter.vote(mq, mt, n_dev, detail_min_count=self.vote_threshold)
         if self._aff is None:
             self._aff = E.AffineResult(hough, self.vote_threshold, self.device)
         aff = E.affine_verify(self.scene, mq, mt, hough, self.vote_threshold, self.affine_threshold,
