@@ -21,7 +21,9 @@ def save_object(obj, filename):
         pickle.dump(obj, outp, pickle.HIGHEST_PROTOCOL)
 
 
-def build_database(image_dir, out_file='training_data.pkl'):
+def build_database(image_dir, out_file='training_data.pkl', packed_file=None):
+    """Writes the reference's pickle; with packed_file also the array form that loads straight into
+    HBM (sod_b200/database.py), which main.Main.load_database reads as well."""
     sift = cv2.SIFT_create()
     data = []
     for name in os.listdir(image_dir):
@@ -34,8 +36,12 @@ def build_database(image_dir, out_file='training_data.pkl'):
         kp, des = sift.detectAndCompute(gray, None)
         data.append([make_temp_kp(kp), des, img_size, get_centroid(kp), os.path.join(image_dir, name)])
     save_object(data, out_file)
+    if packed_file is not None:
+        from sod_b200.database import PackedDatabase
+        PackedDatabase.from_reference_rows(data).save(packed_file)
     return data
 
 
 if __name__ == "__main__":
-    build_database(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else 'training_data.pkl')
+    build_database(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else 'training_data.pkl',
+                   sys.argv[3] if len(sys.argv) > 3 else None)

@@ -7,8 +7,6 @@ libsod_b200.so (no CPU path):
     apply_affine_parameters   -> per-bin fit / prune fixed point            (csrc/sod_affine.cu)
 OpenCV SIFT remains the feature extractor.  matplotlib is optional.
 """
-import pickle
-
 import cv2
 import numpy as np
 
@@ -21,8 +19,8 @@ from VisualHelperFunctions import *  # noqa: F401,F403
 
 from PoseBin import PoseBin
 from PostProcessing import find_max_orientation, get_final_pose, group_orientation, group_position
-from SiftHelperFunctions import make_kp
 from VisualHelperFunctions import show_keypoints, show_object
+from sod_b200 import database as _database
 from sod_b200 import dropin as _dropin
 from sod_b200 import engine as _engine
 
@@ -65,17 +63,15 @@ class Main:
         self.gray_query = cv2.cvtColor(image_query, cv2.COLOR_BGR2GRAY)
         self.kp_query, self.des_query = sift.detectAndCompute(self.gray_query, None)
         self.image_query_size = (len(self.gray_query[0]), len(self.gray_query))
-        with open(training_data_path, 'rb') as inp:
-            data = pickle.load(inp)
-        temp_kp, descs = [], []
-        self.img_size_list, self.img_centroid_list = [], []
-        for datum in data:  # rows: [temp_kp, des, img_size, centroid, path]
-            temp_kp.extend(datum[0])
-            self.img_size_list.extend([datum[2]] * len(datum[0]))
-            self.img_centroid_list.extend([datum[3]] * len(datum[0]))
-            descs.append(datum[1])
-        self.kp = make_kp(temp_kp)
-        self.des = np.concatenate(descs, axis=0)
+        self.load_database(training_data_path)
+
+    def load_database(self, training_data_path=TRAINING_DATA_PATH):
+        """Model database: the reference pickle (main.py:50-66) or the packed array file
+        GenerateDatabaseInfo.build_database(..., packed_file=...) writes (sod_b200/database.py)."""
+        db = _database.PackedDatabase.open(training_data_path)
+        self.img_size_list, self.img_centroid_list = db.per_keypoint_lists()
+        self.kp = db.keypoints()
+        self.des = db.des  # u8; the reference holds the same integers as float32
 
     def _matcher(self):
         if self._db_cache is None or self._db_cache[0] is not self.des:

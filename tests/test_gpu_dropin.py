@@ -110,3 +110,28 @@ def test_run_matcher_needs_two_train_rows():
     m.des = m.des[:1]
     with pytest.raises(ValueError):
         m.run_matcher()
+
+
+def test_main_loads_the_packed_database_and_the_reference_pickle(tmp_path):
+    """Main.load_database on either file format gives the same matches as setting the fields by hand."""
+    from sod_b200.database import PackedDatabase
+    z = np.load(GOLD / "scene_multi.npz")
+    n = len(z["in_m_xy"])
+    db = PackedDatabase(
+        des=z["in_m_des"].astype(np.uint8), xy=z["in_m_xy"].astype(np.float32), size=z["in_m_size"].astype(np.float32),
+        angle=z["in_m_angle"].astype(np.float32), response=np.zeros(n, np.float32),
+        octave=z["in_m_octave"].astype(np.int32), class_id=np.arange(n, dtype=np.int32),
+        image=z["in_m_image"].astype(np.int32), img_size=z["in_img_size"].astype(np.int32),
+        img_centroid=z["in_img_centroid"].astype(np.float64),
+        img_path=np.asarray([f"m{i}.jpg" for i in range(len(z["in_img_size"]))], dtype=str))
+    db.save(tmp_path / "db.sodb")
+    db.to_pickle(tmp_path / "db.pkl")
+    for path in (tmp_path / "db.sodb", tmp_path / "db.pkl"):
+        m = _main_for(z)
+        m.kp, m.des, m.img_size_list, m.img_centroid_list = [], [], [], []
+        m.load_database(path)
+        m.run_matcher()
+        assert [t[1].class_id for t in m.matching_keypoints] == z["match_q"].tolist()
+        assert [t[0].class_id for t in m.matching_keypoints] == z["match_t"].tolist()
+        assert [t[2] for t in m.matching_keypoints] == [tuple(int(v) for v in z["in_img_size"][z["in_m_image"][t]])
+                                                        for t in z["match_t"]]
