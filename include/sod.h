@@ -91,6 +91,40 @@ int sod_top2_merge(const int32_t* parts_idx, const uint32_t* parts_d2, int32_t n
                    int64_t n_query, int32_t* out_idx, uint32_t* out_d2, float* out_dist,
                    uint8_t* out_pass, double ratio, sod_stream_t stream);
 
+/* ---- bf16 fallback for descriptors that are NOT integer-valued 0..255 (non-OpenCV extractors,
+ * normalised float descriptors).  Same reference call as sod_match_top2 (main.py:70-73), approximate
+ * distances: d^2 = |q|^2 + |t|^2 - 2 q.t with fp32 norms and the dot product on tcgen05 kind::f16
+ * (bf16 x bf16 -> f32).  split = 1 (recommended) multiplies bf16 hi/lo halves of both sides
+ * (K = 384); split = 0 is plain bf16 (K = 128).  Stated tolerance on d^2 relative to
+ * |q|^2 + |t|^2: 2e-5 (split) / 4e-3 (plain); indices are those of the two smallest approximate
+ * distances, ties -> lowest index. */
+
+/* Operand row length in bf16 elements: 128 (split = 0) or 384 (split = 1). */
+int64_t sod_bf16_operand_cols(int32_t split);
+/* Rows of the database-side operand / norm arrays: n_rows rounded up to whole 128-row tiles. */
+int64_t sod_bf16_db_rows(int64_t n_rows);
+
+/* float32 [n_rows][128] -> bf16 operand and fp32 squared norms.
+ * side = 0 (query):    dst [n_rows][cols],                   norms [n_rows]
+ * side = 1 (database): dst [sod_bf16_db_rows(n_rows)][cols], norms [sod_bf16_db_rows(n_rows)]
+ *                      (values pre-multiplied by -2, padding rows zero with norm +inf)
+ * *nonfinite_flag (device, may be NULL) is OR-ed with 1 if any input is NaN or infinite. */
+int sod_bf16_prepare(const float* src, int64_t n_rows, int32_t side, int32_t split, uint16_t* dst,
+                     float* norms, int32_t* nonfinite_flag, sod_stream_t stream);
+
+size_t sod_match_bf16_workspace_bytes(int64_t n_query, int64_t n_db);
+
+/* out_idx int32 [n_query][2] (-1 = no such neighbour), out_d2 float32 [n_query][2] (+inf then). */
+int sod_match_top2_bf16(const uint16_t* q_op, const float* qn, int64_t n_query, const uint16_t* db_op,
+                        const float* dn, int64_t n_db, int32_t split, int32_t db_index_base,
+                        int32_t* out_idx, float* out_d2, void* workspace, size_t workspace_bytes,
+                        sod_stream_t stream);
+
+/* sod_top2_merge for float distances (shard merge + ratio test of the bf16 path). */
+int sod_top2_merge_f32(const int32_t* parts_idx, const float* parts_d2, int32_t n_parts,
+                       int64_t n_query, int32_t* out_idx, float* out_d2, float* out_dist,
+                       uint8_t* out_pass, double ratio, sod_stream_t stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * Hough voting and affine verification

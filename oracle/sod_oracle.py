@@ -58,6 +58,36 @@ def knn2(q: np.ndarray, db: np.ndarray, chunk: int = 2048):
     return idx, d2o
 
 
+def knn2_float(q: np.ndarray, db: np.ndarray, chunk: int = 1024):
+    """knn2 for arbitrary float32 descriptors: same call (main.py:70-71), squared distances as
+    float64 sums of the exact float64 differences (cv2 accumulates the same differences in float32).
+    The checker for the bf16 path's stated tolerance.  Returns (idx int32 [nq,2], d2 float64 [nq,2],
+    inf / -1 where the database is too small)."""
+    q = np.ascontiguousarray(q, np.float64)
+    db = np.ascontiguousarray(db, np.float64)
+    nq, n = q.shape[0], db.shape[0]
+    idx = np.full((nq, 2), -1, np.int32)
+    d2o = np.full((nq, 2), np.inf, np.float64)
+    if nq == 0 or n == 0:
+        return idx, d2o
+    for s in range(0, nq, chunk):
+        qc = q[s:s + chunk]
+        d2 = np.empty((qc.shape[0], n))
+        for t in range(0, n, 8192):                      # direct differences: no cancellation
+            diff = qc[:, None, :] - db[None, t:t + 8192, :]
+            d2[:, t:t + 8192] = np.einsum("ijk,ijk->ij", diff, diff)
+        r = np.arange(d2.shape[0])
+        i1 = d2.argmin(1)
+        idx[s:s + chunk, 0] = i1
+        d2o[s:s + chunk, 0] = d2[r, i1]
+        if n >= 2:
+            d2[r, i1] = np.inf
+            i2 = d2.argmin(1)
+            idx[s:s + chunk, 1] = i2
+            d2o[s:s + chunk, 1] = d2[r, i2]
+    return idx, d2o
+
+
 def match_distance(d2: np.ndarray) -> np.ndarray:
     """DMatch.distance: float32 sqrt of the float32 squared distance."""
     return np.sqrt(np.maximum(d2, 0).astype(np.float32))

@@ -23,13 +23,12 @@
 // rejects almost every chunk after the first few thousand columns.  Inside a tile rows are ordered
 // by original index and a permutation maps back, so results (incl. ties -> lowest original index,
 // as cv2) do not depend on the reordering.
-#include <cudaTypedefs.h>
-
 #include <climits>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "sod_common.cuh"
 #include "sod_ptx.cuh"
+#include "sod_tma.cuh"
 
 // Epilogue organisation (compile-time experiment switch; all three give identical results):
 //   1 = 8 warps: (lane quadrant x query half), 128 columns per tile, slot released right after the load
@@ -674,38 +673,10 @@ Plan make_plan(int64_t nq, int64_t ndb, int sms) {
   return p;
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
-            cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }();
-  return fn;
-}
-
 // [n_rows,128] u8 row-major, boxes of 128 rows x 128 B, 128-byte swizzle, OOB rows read as zero.
 int make_desc_map(CUtensorMap* m, const uint8_t* ptr, int64_t n_rows) {
-  auto fn = get_encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return SOD_ERR_CUDA;
-  }
-  const cuuint64_t dims[2] = {SOD_DESC_DIM, static_cast<cuuint64_t>(n_rows)};
-  const cuuint64_t strides[1] = {SOD_DESC_DIM};
-  const cuuint32_t box[2] = {SOD_DESC_DIM, kTileN};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(ptr), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
-    return SOD_ERR_CUDA;
-  }
-  return SOD_OK;
+  return make_rowmajor_map(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ptr, n_rows, SOD_DESC_DIM, SOD_DESC_DIM,
+                           kTileN);
 }
 
 }  // namespace

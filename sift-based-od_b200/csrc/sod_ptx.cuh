@@ -131,6 +131,17 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> f32 (SASS: UTCHMMA), K = 16 per instruction.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued UMMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -212,6 +223,14 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_u8(int m, int n) {
   return (2u << 4)                               // c_format = S32
          | (0u << 7) | (0u << 10)                // a_format = b_format = unsigned 8-bit
+         | (static_cast<uint32_t>(n >> 3) << 17) // N / 8
+         | (static_cast<uint32_t>(m >> 4) << 24);  // M / 16
+}
+
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4)                               // c_format = F32
+         | (1u << 7) | (1u << 10)                // a_format = b_format = BF16
          | (static_cast<uint32_t>(n >> 3) << 17) // N / 8
          | (static_cast<uint32_t>(m >> 4) << 24);  // M / 16
 }

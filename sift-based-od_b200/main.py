@@ -73,19 +73,33 @@ class Main:
         self.kp = db.keypoints()
         self.des = db.des  # u8; the reference holds the same integers as float32
 
-    def _matcher(self):
+    def _matcher(self, exact=True):
+        """Resident database for the exact u8 path, or for the bf16 path when either side holds
+        non-integer descriptors (cached per self.des object and path)."""
+        key = "u8" if exact else "f32"
         if self._db_cache is None or self._db_cache[0] is not self.des:
-            shard = _engine.prepare_db(_engine.pack_descriptors(self.des))
-            self._db_cache = (self.des, _engine.Matcher(shard))
-        return self._db_cache[1]
+            self._db_cache = (self.des, {})
+        cache = self._db_cache[1]
+        if key not in cache:
+            if exact:
+                cache[key] = _engine.Matcher(_engine.prepare_db(_engine.pack_descriptors(self.des)))
+            else:
+                des = _engine.torch.as_tensor(np.ascontiguousarray(self.des, dtype=np.float32)).cuda()
+                cache[key] = _engine.FloatMatcher(_engine.prepare_db_float(des))
+        return cache[key]
 
     def run_matcher(self):
-        """knnMatch(k=2) + ratio 0.75 (main.py:68-86)."""
+        """knnMatch(k=2) + ratio 0.75 (main.py:68-86).  Integer-valued descriptors (what OpenCV SIFT
+        produces) take the exact u8 path; anything else the bf16 path with its stated tolerance."""
         n_train = len(self.des)
         if n_train < 2:  # the reference's `for m, n in matches` cannot unpack (SURVEY T7)
             raise ValueError("not enough values to unpack (expected 2, got %d)" % n_train)
-        q = _engine.pack_descriptors(self.des_query)
-        idx, _, _, ok = _engine.knn_match_ratio(q, self._matcher())
+        try:
+            q = _engine.pack_descriptors(self.des_query)
+            idx, _, _, ok = _engine.knn_match_ratio(q, self._matcher(exact=True))
+        except _engine.NonIntegerDescriptors:
+            q = _engine.torch.as_tensor(np.ascontiguousarray(self.des_query, dtype=np.float32)).cuda()
+            idx, _, _, ok = _engine.knn_match_ratio_float(q, self._matcher(exact=False))
         idx = idx.cpu().numpy()
         for qi in np.nonzero(ok.cpu().numpy())[0]:
             t = int(idx[qi, 0])

@@ -51,9 +51,13 @@ def pack_descriptors(des, device: torch.device | str = "cuda") -> torch.Tensor:
     check(lib.sod_pack_u8_from_f32(_ptr(src), src.shape[0], _ptr(dst), _ptr(flag), _stream()),
           "sod_pack_u8_from_f32")
     if int(flag.item()) != 0:
-        raise ValueError("descriptors are not integer-valued in 0..255: the exact u8 tensor-core path "
-                         "does not apply (bf16 path not built)")
+        raise NonIntegerDescriptors("descriptors are not integer-valued in 0..255: the exact u8 tensor-core "
+                                    "path does not apply (use prepare_db_float / FloatMatcher)")
     return dst
+
+
+class NonIntegerDescriptors(ValueError):
+    """Raised by pack_descriptors for float descriptors the exact u8 path cannot represent."""
 
 
 @dataclass
@@ -142,6 +146,96 @@ def knn_match_ratio(q_u8: torch.Tensor, matcher: Matcher, ratio: float = RATIO):
     """Single-shard convenience: knnMatch(k=2) + ratio flags."""
     idx, d2 = matcher.top2(q_u8)
     return merge_top2(idx[None], d2[None], ratio)
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 fallback for non-integer descriptors (approximate distances, tolerance stated in sod.h)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class FloatShard:
+    """Database slice for the bf16 path: operand [tiles*128, cols] (pre-multiplied by -2) + fp32 norms."""
+    op: torch.Tensor         # bf16 bits as int16 [tiles*128, cols]
+    norms: torch.Tensor      # f32 [tiles*128], +inf on padding rows
+    n_rows: int
+    index_base: int
+    split: bool
+
+    @property
+    def n(self) -> int:
+        return self.n_rows
+
+
+def _bf16_prepare(des_f32: torch.Tensor, side: int, split: bool):
+    des_f32 = _require_cuda(des_f32, torch.float32, "float descriptors")
+    n = int(des_f32.shape[0])
+    dev = des_f32.device
+    cols = int(lib.sod_bf16_operand_cols(int(split)))
+    rows = int(lib.sod_bf16_db_rows(n)) if side else n
+    op = torch.empty((max(rows, 1), cols), dtype=torch.int16, device=dev)
+    norms = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.sod_bf16_prepare(_ptr(des_f32), n, side, int(split), _ptr(op), _ptr(norms), _ptr(flag), _stream()),
+          "sod_bf16_prepare")
+    if int(flag.item()) != 0:
+        raise ValueError("descriptors contain NaN or infinite values")
+    return op, norms
+
+
+def prepare_db_float(des_f32: torch.Tensor, index_base: int = 0, split: bool = True) -> FloatShard:
+    op, norms = _bf16_prepare(des_f32, 1, split)
+    return FloatShard(op, norms, int(des_f32.shape[0]), int(index_base), bool(split))
+
+
+class FloatMatcher:
+    """2-NN matcher of the bf16 path for one database shard."""
+
+    def __init__(self, shard: FloatShard):
+        self.shard = shard
+        self._ws: torch.Tensor | None = None
+        self.events: list | None = None
+
+    def top2(self, q_f32: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """-> (idx int32 [nq,2] global rows or -1, d2 float32 [nq,2] approximate squared distances)."""
+        s = self.shard
+        q_op, qn = _bf16_prepare(q_f32, 0, s.split)
+        nq = int(q_f32.shape[0])
+        need = int(lib.sod_match_bf16_workspace_bytes(nq, s.n))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=q_op.device)
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=q_op.device)
+        d2 = torch.empty((nq, 2), dtype=torch.float32, device=q_op.device)
+        if self.events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(lib.sod_match_top2_bf16(_ptr(q_op), _ptr(qn), nq, _ptr(s.op), _ptr(s.norms), s.n, int(s.split),
+                                      s.index_base, _ptr(idx), _ptr(d2), _ptr(self._ws), self._ws.numel(),
+                                      _stream()), "sod_match_top2_bf16")
+        if self.events is not None:
+            e1.record()
+            self.events.append((e0, e1))
+        return idx, d2
+
+
+def merge_top2_float(parts_idx: torch.Tensor, parts_d2: torch.Tensor, ratio: float = RATIO):
+    """[G,nq,2] float candidate lists -> (idx, d2 f32, dist f32, pass u8)."""
+    parts_idx = _require_cuda(parts_idx, torch.int32, "parts_idx")
+    parts_d2 = _require_cuda(parts_d2, torch.float32, "parts_d2")
+    if parts_idx.ndim == 2:
+        parts_idx, parts_d2 = parts_idx[None], parts_d2[None]
+    g, nq = int(parts_idx.shape[0]), int(parts_idx.shape[1])
+    dev = parts_idx.device
+    idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    d2 = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    ok = torch.empty(nq, dtype=torch.uint8, device=dev)
+    check(lib.sod_top2_merge_f32(_ptr(parts_idx), _ptr(parts_d2), g, nq, _ptr(idx), _ptr(d2), _ptr(dist),
+                                 _ptr(ok), float(ratio), _stream()), "sod_top2_merge_f32")
+    return idx, d2, dist, ok
+
+
+def knn_match_ratio_float(q_f32: torch.Tensor, matcher: FloatMatcher, ratio: float = RATIO):
+    idx, d2 = matcher.top2(q_f32)
+    return merge_top2_float(idx[None], d2[None], ratio)
 
 
 # ------------------------------------------------------------------------------------------------

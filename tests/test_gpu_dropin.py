@@ -135,3 +135,15 @@ def test_main_loads_the_packed_database_and_the_reference_pickle(tmp_path):
         assert [t[0].class_id for t in m.matching_keypoints] == z["match_t"].tolist()
         assert [t[2] for t in m.matching_keypoints] == [tuple(int(v) for v in z["in_img_size"][z["in_m_image"][t]])
                                                         for t in z["match_t"]]
+
+
+def test_main_takes_the_bf16_path_for_non_integer_descriptors():
+    """Halved descriptors are non-integer -> bf16 path; every product stays exact, so the matches
+    are the golden ones."""
+    z = np.load(GOLD / "scene_multi.npz")
+    m = _main_for(z)
+    m.des = m.des * np.float32(0.5)
+    m.des_query = m.des_query * np.float32(0.5)
+    m.run_matcher()
+    assert [t[1].class_id for t in m.matching_keypoints] == z["match_q"].tolist()
+    assert [t[0].class_id for t in m.matching_keypoints] == z["match_t"].tolist()
