@@ -43,6 +43,24 @@ def run(nq, ndb, iters=10, kind="uniform"):
           f"{nq / ms * 1e3 / 1e6:8.3f} Mq/s", flush=True)
 
 
+def run_float(nq, ndb, split, iters=10):
+    """bf16 fallback path on RootSIFT-style float descriptors; the timed region is the match kernel
+    call alone (operands prepared outside)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q = sift_like_gpu(nq, g).float().sqrt_()
+    db = sift_like_gpu(ndb, g).float().sqrt_()
+    m = E.FloatMatcher(E.prepare_db_float(db, split=split))
+    m.events = []
+    for _ in range(3 + iters):
+        m.top2(q)
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in m.events[3:]]
+    ms = float(np.median(ts))
+    k = 384 if split else 128
+    print(f"bf16 split={int(split)} nq={nq:>8} ndb={ndb:>8}  {ms:9.3f} ms (min {min(ts):.3f})  "
+          f"{2.0 * nq * ndb * k / ms / 1e9:8.1f} TFLOP/s issued  {nq / ms * 1e3 / 1e6:8.3f} Mq/s", flush=True)
+
+
 if __name__ == "__main__":
     shapes = [(10000, 100000), (10000, 1000000), (65536, 1000000)]
     if len(sys.argv) > 1:
@@ -50,4 +68,7 @@ if __name__ == "__main__":
     kinds = os.environ.get("SOD_BENCH_KINDS", "uniform,sift").split(",")
     for kind in kinds:
         for nq, ndb in shapes:
-            run(nq, ndb, kind=kind)
+            if kind in ("bf16", "bf16x3"):
+                run_float(nq, ndb, kind == "bf16x3")
+            else:
+                run(nq, ndb, kind=kind)
