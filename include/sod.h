@@ -160,6 +160,7 @@ typedef struct {
 #define SOD_SIGMA_LUT_MIN (-24)
 #define SOD_SIGMA_LUT_LEN 49
 #define SOD_MAX_BINS 15 /* bins^4 uint32 counters must fit one SM's shared memory */
+#define SOD_MAX_CLUSTER_BINS 65536 /* sod_pose_adjacency / sod_angle_adjacency: n x n/8 bytes of bit matrix */
 
 /* Outputs of sod_hough_vote (device).  Bin records are compact and in no particular order;
  * `bin_order` reproduces the reference's dict insertion order when sorted ascending. */
@@ -248,6 +249,26 @@ int sod_affine_verify(const sod_scene* scene, const int32_t* match_q, const int3
 int sod_affine_residual_keep(const float* model_xy, const float* query_xy, int64_t n,
                              const double* params, double x_ref, double y_ref, uint8_t* keep,
                              sod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pose clustering after the path
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Neighbour graph of group_position (PostProcessing.py:14-37) over n surviving bins: bins a, b are
+ * adjacent iff |cx_a - cx_b| <= reach_x_a, reach_x_b and |cy_a - cy_b| <= reach_y_a, reach_y_b, with
+ * reach_x = img_w * scale / 4 and reach_y = img_h * scale / 4 evaluated by the caller (fp64, the
+ * reference's expression).  segment (may be NULL) restricts edges to bins of equal segment id
+ * (e.g. the frame of a batch).  adj: uint32 [n][ceil(n/32)] bit matrix, bit j of row i (no self
+ * loops); label[i] = lowest bin index of i's connected component.  n <= SOD_MAX_CLUSTER_BINS. */
+int sod_pose_adjacency(const double* cx, const double* cy, const double* reach_x, const double* reach_y,
+                       const int32_t* segment, int64_t n, uint32_t* adj, int32_t* label,
+                       sod_stream_t stream);
+
+/* Neighbour graph of group_orientation (PostProcessing.py:39-63): bins of equal segment (the
+ * position cluster) are adjacent iff abs(math.degrees(angle_a - angle_b)) <= max_degrees (1 in the
+ * reference).  Same outputs as sod_pose_adjacency. */
+int sod_angle_adjacency(const double* angle, const int32_t* segment, int64_t n, double max_degrees,
+                        uint32_t* adj, int32_t* label, sod_stream_t stream);
 
 #ifdef __cplusplus
 }

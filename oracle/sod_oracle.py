@@ -363,6 +363,88 @@ def affine_verify(scene: Scene, match_q, match_t, bins_list, threshold: int = 4,
     return live
 
 
+# --------------------------------------------------------------------------------------------------
+# Post-processing: PostProcessing.py:4-112 on arrays
+# --------------------------------------------------------------------------------------------------
+def _preorder_components(n: int, nbrs) -> list:
+    """Components of an undirected graph in the reference's visiting order: start nodes ascending,
+    recursive pre-order dfs (PostProcessing.py:4-11) over neighbour lists that are ascending by
+    construction (:17-30); written iteratively so large clusters do not hit the recursion limit."""
+    seen = [False] * n
+    comps = []
+    for s in range(n):
+        if seen[s]:
+            continue
+        seen[s] = True
+        comp = [s]
+        stack = [(s, 0)]
+        while stack:
+            v, k = stack.pop()
+            lst = nbrs[v]
+            while k < len(lst) and seen[lst[k]]:
+                k += 1
+            if k < len(lst):
+                nb = lst[k]
+                stack.append((v, k + 1))
+                seen[nb] = True
+                comp.append(nb)
+                stack.append((nb, 0))
+        comps.append(comp)
+    return comps
+
+
+def post_process(cx, cy, scale, angle, img_w, img_h):
+    """group_position -> group_orientation -> find_max_orientation -> get_final_pose on n surviving
+    bins given as arrays (centroid, scale, angle = PoseBin running means; img_w/img_h = model image
+    size).  Returns (clusters, sub_clusters, orientations, final) with bins as indices:
+    clusters[c] = bin indices in visiting order; sub_clusters[c] = lists of bin indices;
+    final[c] = (cx, cy, orientation, scale, w, h)."""
+    n = len(cx)
+    cx = [float(v) for v in cx]; cy = [float(v) for v in cy]
+    scale = [float(v) for v in scale]; angle = [float(v) for v in angle]
+    # Python ints stay ints in `img_size[0] * scale / 4` (int * float), as in the reference
+    nbrs = [[] for _ in range(n)]
+    for b in range(n):                                       # PostProcessing.py:17-30
+        for a in range(b):
+            dx, dy = abs(cx[a] - cx[b]), abs(cy[a] - cy[b])
+            if dx <= img_w[a] * scale[a] / 4 and dy <= img_h[a] * scale[a] / 4 and \
+                    dx <= img_w[b] * scale[b] / 4 and dy <= img_h[b] * scale[b] / 4:
+                nbrs[b].append(a)
+                nbrs[a].append(b)
+    clusters = _preorder_components(n, nbrs)
+    sub_clusters, orientations, final = [], [], []
+    for cl in clusters:
+        m = len(cl)
+        g = [[] for _ in range(m)]
+        for b in range(m):                                   # :43-56, positions within the cluster list
+            for a in range(b):
+                if abs(math.degrees(angle[cl[a]] - angle[cl[b]])) <= 1:
+                    g[a].append(b)
+                    g[b].append(a)
+        subs = [[cl[p] for p in comp] for comp in _preorder_components(m, g)]
+        sub_clusters.append(subs)
+        best, ori = 0, 0                                     # :65-82 (later sub-clusters win ties)
+        for sub in subs:
+            if len(sub) >= best:
+                best = len(sub)
+                ori = 0
+                for i in sub:
+                    ori += angle[i]
+                ori = ori / len(sub)
+        orientations.append(ori)
+        sx = sy = ss = 0                                     # :86-112
+        min_area, shape = math.inf, (0, 0)
+        for i in cl:
+            sx += cx[i]
+            sy += cy[i]
+            ss += scale[i]
+            area = (img_w[i] * scale[i]) * (img_h[i] * scale[i])
+            if area < min_area:
+                min_area, shape = area, (img_w[i], img_h[i])
+        final.append((sx / m, sy / m, ori, ss / m, shape[0], shape[1]))
+    return clusters, sub_clusters, orientations, final
+
+
 def pipeline(scene: Scene, q_des, db_des, bins: int = 15, vote_threshold: int = 5,
              affine_threshold: int = 4):
     """main.py:180-185 end to end on arrays: match -> ratio -> vote -> valid bins -> affine."""

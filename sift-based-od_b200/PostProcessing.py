@@ -1,15 +1,18 @@
-"""Pose clustering after the hot path, drop-in for PostProcessing.py:4-112.
+"""Pose clustering after the hot path, drop-in for PostProcessing.py:4-112 (SURVEY.md §8f N1).
 
-Host-side for now (it runs on the tens-hundreds of bins that survive the affine
-stage).  Same neighbour rule, same visiting order and therefore the same clusters and float sums as
-the reference, but the depth-first walk is iterative, so large clusters no longer hit Python's
-recursion limit.
+Same functions, arguments and return structures as the reference.  The O(V^2) neighbour tests of
+group_position / group_orientation run on the GPU (sod_pose_adjacency / sod_angle_adjacency,
+csrc/sod_cluster.cu); the clusters, their order and the order of every float sum are the
+reference's (sod_b200/postprocess.py recovers its depth-first visiting order from the adjacency
+bit rows), and large clusters no longer hit Python's recursion limit.
 """
 import math
 
+from sod_b200 import postprocess as _pp
+
 
 def dfs(i, seen, graph, out, items):
-    """Pre-order depth-first walk from i appending items[...] to out (reference :4-11)."""
+    """Pre-order depth-first walk from i appending items[...] to out (reference :4-11), iterative."""
     if i in seen:
         return out
     seen.add(i)
@@ -27,48 +30,20 @@ def dfs(i, seen, graph, out, items):
     return out
 
 
-def _components(n, graph, items):
-    seen = set()
-    groups = []
-    for i in range(n):
-        if i not in seen:
-            groups.append(dfs(i, seen, graph, [], items))
-    return groups
-
-
 def group_position(valid_bins):
     """Clusters of bins whose centroids are mutually within a quarter of the (scaled) model size in
     x and y (reference :14-37)."""
-    n = len(valid_bins)
-    graph = {b: [] for b in range(n)}
-    for b in range(n):
-        xb, yb = valid_bins[b].centroid
-        wb = valid_bins[b].img_size[0] * valid_bins[b].scale / 4
-        hb = valid_bins[b].img_size[1] * valid_bins[b].scale / 4
-        for a in range(b):
-            xa, ya = valid_bins[a].centroid
-            dx, dy = abs(xa - xb), abs(ya - yb)
-            if dx <= valid_bins[a].img_size[0] * valid_bins[a].scale / 4 and \
-                    dy <= valid_bins[a].img_size[1] * valid_bins[a].scale / 4 and dx <= wb and dy <= hb:
-                graph[b].append(a)
-                graph[a].append(b)
-    return _components(n, graph, valid_bins)
+    clusters, _ = _pp.cluster_positions([b.centroid[0] for b in valid_bins], [b.centroid[1] for b in valid_bins],
+                                        [b.scale for b in valid_bins], [b.img_size[0] for b in valid_bins],
+                                        [b.img_size[1] for b in valid_bins])
+    return [[valid_bins[i] for i in cl] for cl in clusters]
 
 
 def group_orientation(pose_cluster):
     """Inside every position cluster, sub-clusters of bins whose mean angles differ by <= 1 degree
     (reference :39-63)."""
-    result = []
-    for cluster in pose_cluster:
-        n = len(cluster)
-        graph = {b: [] for b in range(n)}
-        for b in range(n):
-            for a in range(b):
-                if abs(math.degrees(cluster[a].angle - cluster[b].angle)) <= 1:
-                    graph[a].append(b)
-                    graph[b].append(a)
-        result.append(_components(n, graph, cluster))
-    return result
+    pos = _pp.orientation_subclusters([[b.angle for b in cluster] for cluster in pose_cluster])
+    return [[[cluster[p] for p in comp] for comp in comps] for cluster, comps in zip(pose_cluster, pos)]
 
 
 def find_max_orientation(orientation_cluster):

@@ -79,6 +79,8 @@ _PROTOS = {
     "sod_match_bf16_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "sod_match_top2_bf16": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _p, _p, C.c_size_t, _p]),
     "sod_top2_merge_f32": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, _p, C.c_double, _p]),
+    "sod_pose_adjacency": (C.c_int, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "sod_angle_adjacency": (C.c_int, [_p, _p, _i64, C.c_double, _p, _p, _p]),
     "sod_compact_scratch_bytes": (C.c_size_t, [_i64]),
     "sod_compact_matches": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p]),
     "sod_estimate_pose": (C.c_int, [C.POINTER(Scene), _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),

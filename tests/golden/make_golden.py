@@ -117,7 +117,68 @@ SCENES = {
 }
 
 
+def postprocess_bins(seed=21, n=420):
+    """Surviving-bin statistics for the post-processing fixture: several object instances, each a
+    cloud of bins around its centre (chains of neighbours, touching clusters, values exactly on the
+    <= thresholds, orientation runs 1 degree apart), plus isolated bins."""
+    rng = np.random.default_rng(seed)
+    cx, cy, sc, an, w, h = [], [], [], [], [], []
+    sizes = [(1500, 1000), (1500, 2000), (1500, 1125)]
+    for inst in range(7):
+        m = int(rng.integers(20, 110))
+        size = sizes[inst % 3]
+        s0 = float(2.0 ** rng.integers(-2, 1))
+        x0, y0 = 800 + 1500.0 * inst + rng.uniform(-60, 60), rng.uniform(300, 2700)
+        spread = size[0] * s0 / 4
+        cx += list(x0 + rng.uniform(-1.2, 1.2, m) * spread)
+        cy += list(y0 + rng.uniform(-1.2, 1.2, m) * size[1] * s0 / 4)
+        sc += list(s0 * rng.choice([0.5, 1.0, 1.0, 1.0, 2.0], m))
+        a0 = rng.uniform(0, 2 * np.pi)
+        an += list(a0 + np.radians(rng.choice([0.0, 0.4, 0.9, 1.0, 1.7, 2.5, 30.0], m)
+                                   + rng.uniform(-0.05, 0.05, m)))
+        w += [size[0]] * m
+        h += [size[1]] * m
+    k = max(n - len(cx), 40)
+    cx += list(rng.uniform(0, 12000, k)); cy += list(rng.uniform(0, 3000, k))
+    sc += list(2.0 ** rng.integers(-2, 3, k).astype(np.float64)); an += list(rng.uniform(0, 2 * np.pi, k))
+    w += [1500] * k; h += [1000] * k
+    cx, cy, sc, an = (np.asarray(v, np.float64) for v in (cx, cy, sc, an))
+    # exact-threshold cases: bin 1 sits exactly reach_x away from bin 0, bin 3 exactly 1 degree from bin 2
+    sc[0] = sc[1] = 1.0; w[0] = w[1] = 1500; h[0] = h[1] = 1000
+    cx[1] = cx[0] + 375.0; cy[1] = cy[0]
+    an[3] = an[2] + np.radians(1.0)
+    perm = rng.permutation(len(cx))
+    return cx[perm], cy[perm], sc[perm], an[perm], np.asarray(w, np.int64)[perm], np.asarray(h, np.int64)[perm]
+
+
+def make_postprocess():
+    """tests/golden/postprocess.npz: the reference's PostProcessing functions on the bins above."""
+    import_reference()
+    import PostProcessing as ref_pp  # the reference's module
+    cx, cy, sc, an, w, h = postprocess_bins()
+    bins = [types.SimpleNamespace(centroid=(float(cx[i]), float(cy[i])), scale=float(sc[i]), angle=float(an[i]),
+                                  img_size=(int(w[i]), int(h[i])), index=i) for i in range(len(cx))]
+    pose_cluster = ref_pp.group_position(bins)
+    ori_cluster = ref_pp.group_orientation(pose_cluster)
+    ori = ref_pp.find_max_orientation(ori_cluster)
+    final = ref_pp.get_final_pose(pose_cluster, ori)
+    cl_off = np.cumsum([0] + [len(c) for c in pose_cluster])
+    subs = [sub for c in ori_cluster for sub in c]
+    sub_off = np.cumsum([0] + [len(sub) for sub in subs])
+    np.savez_compressed(
+        HERE / "postprocess.npz", cx=cx, cy=cy, scale=sc, angle=an, img_w=w, img_h=h,
+        cluster_off=cl_off, cluster_members=np.array([b.index for c in pose_cluster for b in c], np.int32),
+        subs_per_cluster=np.array([len(c) for c in ori_cluster], np.int32), sub_off=sub_off,
+        sub_members=np.array([b.index for sub in subs for b in sub], np.int32),
+        orientation=np.array(ori, np.float64),
+        final=np.array([[c[0], c[1], o, s, sh[0], sh[1]] for (c, o, s, sh) in final], np.float64))
+    print("postprocess bins", len(bins), "clusters", len(pose_cluster), "largest", max(len(c) for c in pose_cluster),
+          "sub-clusters", len(subs))
+
+
 def main():
+    if "--postprocess-only" in sys.argv:
+        return make_postprocess()
     refmain = import_reference()
     import cv2
     for name, kw in SCENES.items():
@@ -128,6 +189,8 @@ def main():
                             versions=np.array([cv2.__version__, np.__version__, sys.version.split()[0]]))
         print(name, "matches", len(out["match_q"]), "bins", len(out["bin_votes"]), "valid",
               len(out["valid_keys"]), "live", len(out["live_keys"]), "final", len(out["final_pose"]))
+
+    make_postprocess()
 
     # known-answer facts taken from the reference's own libraries
     import math

@@ -102,3 +102,21 @@ def test_degenerate_sizes():
     idx, d2 = O.knn2(q, np.ones((1, 128), np.uint8))
     assert idx.tolist() == [[0, -1]] * 3 and d2[:, 0].tolist() == [128] * 3
     assert not O.ratio_pass(d2, idx).any()
+
+
+def test_post_process_equals_reference():
+    """oracle.post_process vs the reference's PostProcessing functions (fixture postprocess.npz):
+    cluster membership in visiting order, orientation sub-clusters, orientations and final poses,
+    all bit-exact."""
+    z = np.load(GOLD / "postprocess.npz")
+    clusters, subs, ori, final = O.post_process(z["cx"], z["cy"], z["scale"], z["angle"],
+                                                [int(v) for v in z["img_w"]], [int(v) for v in z["img_h"]])
+    off = z["cluster_off"]
+    assert [len(c) for c in clusters] == np.diff(off).tolist()
+    assert [i for c in clusters for i in c] == z["cluster_members"].tolist()
+    assert [len(s) for s in subs] == z["subs_per_cluster"].tolist()
+    flat = [sub for s in subs for sub in s]
+    assert [len(sub) for sub in flat] == np.diff(z["sub_off"]).tolist()
+    assert [i for sub in flat for i in sub] == z["sub_members"].tolist()
+    np.testing.assert_array_equal(np.array(ori, np.float64), z["orientation"])
+    np.testing.assert_array_equal(np.array(final, np.float64), z["final"])
