@@ -149,7 +149,28 @@ class DetectionPipeline:
         vb = a.valid_bin[:n_valid].long()
         out["valid_group"] = h.bin_group[vb].cpu().numpy()
         out["valid_code"] = h.bin_code[vb].cpu().numpy()
+        out["valid_order"] = h.bin_order[vb].cpu().numpy()
+        out["valid_mean"] = h.bin_mean[vb].cpu().numpy()
         return out
+
+    def final_poses(self, out: dict) -> dict[int, list]:
+        """Main.post_process (main.py:159-168) for every frame of a fetched result: the bins that
+        survived the affine stage are clustered by position and orientation (GPU neighbour graphs,
+        sod_b200/postprocess.py) -> {frame: [((cx, cy), orientation, scale, (w, h)), ...]}.  Bins
+        enter in the reference's order (Hough insertion order inside a space).  With shard="db"
+        this covers the objects of this rank only."""
+        from .postprocess import post_process_arrays
+        live = (out["status"] & 1).astype(bool)
+        group, order, mean = out["valid_group"][live], out["valid_order"][live], out["valid_mean"][live]
+        frame = group // self.scene.groups_per_frame
+        o = np.lexsort((order, group, frame))
+        mean, frame = mean[o], frame[o].astype(np.int32)
+        clusters, _, _, final = post_process_arrays(mean[:, 0], mean[:, 1], mean[:, 3], mean[:, 2], mean[:, 4],
+                                                    mean[:, 5], segment=frame, device=self.device)
+        poses: dict[int, list] = {}
+        for cl, pose in zip(clusters, final):
+            poses.setdefault(int(frame[cl[0]]), []).append(pose)
+        return poses
 
     @staticmethod
     def fetched_bytes(out: dict) -> int:
