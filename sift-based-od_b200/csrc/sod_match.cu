@@ -140,15 +140,18 @@ struct Top2 {
 };
 constexpr long long kNoKey64 = (static_cast<long long>(kNoKey) << 32) | 0x7FFFFFFF;
 
-// One chunk of 32 accumulator columns, in three levels of increasing cost:
+// One chunk of 32 accumulator columns, in levels of increasing cost:
 //  1. bound: every element has |t|^2 - 2 q.t >= cmin - 2*max(acc); if that exceeds the row's 2nd
 //     best nothing can change (~0.5 ALU op per element, tight because the database is norm-sorted);
-//  2. exact: the 32 packed keys ((|t|^2 - 2 q.t) << 8 | tile column) by one IMAD each from the
-//     prepared (|t|^2 << 8 | column), and their minimum (1.5 ops per element);
-//  3. update: branch-free top-2 of the chunk's packed keys (columns inside a tile are in original-
-//     index order, so ties inside the tile resolve correctly), then at most two offers to the
-//     running best with the ORIGINAL row index read through the permutation in shared memory,
-//     which settles ties across tiles exactly as cv2 does (lowest original index).
+//  2. the same bound per sub-tree of the max tree (9 + 9 + 9 + 5 elements, its maxima are already
+//     there): only sub-trees that fail it are looked at;
+//  3. inside those: the exact packed keys ((|t|^2 - 2 q.t) << 8 | tile column) by one IMAD each
+//     from the prepared (|t|^2 << 8 | column) and a running (smallest, 2nd smallest) (columns inside
+//     a tile are in original-index order, so ties inside the tile resolve correctly), then at most
+//     two offers to the running best with the ORIGINAL row index read through the permutation in
+//     shared memory, which settles ties across tiles exactly as cv2 does (lowest original index).
+// The epilogue is bound by ALU issue slots, so the instruction count of this rare path matters: a
+// branch-free 32-key tournament (+53 instructions) cost 5 %, finer sub-trees (more branches) 10 %.
 // All tests are exact; pruning never changes the result.
 // `thr` is the pruning threshold: the row's 2nd best over everything either of its two threads has
 // seen (an element above it cannot be in the merged top-2; ties go through).
@@ -158,36 +161,33 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
 #if SOD_EXP == 1 || SOD_EXP == 2
   return;
 #endif
-  const int amax = max_tree32(reinterpret_cast<const int*>(v));
-  if (cmin - 2 * amax > thr) return;
-  int k[32];
+  // level 1, with the sub-tree maxima of the balanced tree kept: elements 0-8, 9-17, 18-26, 27-31
+  const int* av = reinterpret_cast<const int*>(v);
+  int t[11];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int4 c = cp4[j];
-    k[4 * j + 0] = c.x - 512 * static_cast<int>(v[4 * j + 0]);
-    k[4 * j + 1] = c.y - 512 * static_cast<int>(v[4 * j + 1]);
-    k[4 * j + 2] = c.z - 512 * static_cast<int>(v[4 * j + 2]);
-    k[4 * j + 3] = c.w - 512 * static_cast<int>(v[4 * j + 3]);
-  }
-  // group minima of 4 x 8 keys: the update below only touches groups that hold a candidate
-  int g[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    g[i] = imin3(imin3(k[8 * i], k[8 * i + 1], k[8 * i + 2]), imin3(k[8 * i + 3], k[8 * i + 4], k[8 * i + 5]),
-                 min(k[8 * i + 6], k[8 * i + 7]));
-  if ((min(imin3(g[0], g[1], g[2]), g[3]) >> 8) > thr) return;
+  for (int i = 0; i < 10; ++i) t[i] = imax3(av[3 * i], av[3 * i + 1], av[3 * i + 2]);
+  t[10] = max(av[30], av[31]);
+  const int u0 = imax3(t[0], t[1], t[2]), u1 = imax3(t[3], t[4], t[5]), u2 = imax3(t[6], t[7], t[8]);
+  const int u3 = max(t[9], t[10]);
+  if (cmin - 2 * max(imax3(u0, u1, u2), u3) > thr) return;
+  // levels 2 + 3 only inside the sub-trees whose own bound fails: exact packed keys by one IMAD
+  // each and a running (smallest, 2nd smallest)
+  const int* cp = reinterpret_cast<const int*>(cp4);
   int t1 = INT_MAX, t2 = INT_MAX;
+  auto scan = [&](int lo, int hi) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if ((g[i] >> 8) <= thr) {
-#pragma unroll
-      for (int j = 8 * i; j < 8 * i + 8; ++j) {
-        const int t = max(t1, k[j]);
-        t1 = min(t1, k[j]);
-        t2 = min(t2, t);
-      }
+    for (int j = lo; j < hi; ++j) {
+      const int key = cp[j] - 512 * av[j];
+      const int m = max(t1, key);
+      t1 = min(t1, key);
+      t2 = min(t2, m);
     }
-  }
+  };
+  if (cmin - 2 * u0 <= thr) scan(0, 9);
+  if (cmin - 2 * u1 <= thr) scan(9, 18);
+  if (cmin - 2 * u2 <= thr) scan(18, 27);
+  if (cmin - 2 * u3 <= thr) scan(27, 32);
+  if ((t1 >> 8) > thr) return;
   const int o1 = perm_s[t1 & 0xFF];
   if (o1 >= 0) best.offer(t1 >> 8, idx_base + o1);
   thr = min(thr, best.d2);
