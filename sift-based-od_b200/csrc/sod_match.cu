@@ -38,9 +38,6 @@
 #ifndef SOD_EPI_MODE
 #define SOD_EPI_MODE 2
 #endif
-#ifndef SOD_SHARE_THR
-#define SOD_SHARE_THR 0  // (experiment, +3 % on 125k-row shards, -4 % on 1M) the two threads of a query row exchange their 2nd best through shared memory
-#endif
 #ifndef SOD_EXP
 #define SOD_EXP 0  // kernel experiments (timing only, results invalid): 1 = no epilogue math, 2 = no TMEM loads
 #endif
@@ -84,9 +81,7 @@ constexpr int kBarGroups = SOD_EPI_MODE == 4 ? 3 : 2;  // accumulator barriers a
                                                        // skip a phase)
 constexpr int kNumBars = 2 * kStages + 4 + 4 * kBarGroups + kCqSlots;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr int kOffThr = kOffTmemPtr + 16;                   // [2][kBlockQ] int64: 2nd-best exchange between
-                                                            // the two threads that share a query row
-constexpr int kSmemBytes = kOffThr + 2 * kBlockQ * 8 + 1024;  // +1024: manual 1 KB alignment
+constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // +1024: manual 1 KB alignment
 
 struct MatchArgs {
   const int32_t* qn;   // [nq] |q|^2
@@ -94,6 +89,7 @@ struct MatchArgs {
                        // original row (-1 = padding)
   uint32_t* part_d2;   // [n_seg * 2][nq][2]  (one list per segment and column half)
   int32_t* part_idx;   // [n_seg * 2][nq][2]
+  int32_t* row_thr;    // [n_qblocks * 256] shared pruning thresholds (memset to 0x7F..), or nullptr
   int nq;
   int n_tiles;
   int n_qblocks;
@@ -101,27 +97,10 @@ struct MatchArgs {
   int idx_base;
 };
 
-// Balanced 3-input reduction trees (depth 4) over 32 registers: the serial form is a 16-deep
-// dependent chain of VIMNMX3, which is latency-bound with two epilogue warps per scheduler.
+// 3-input min / max: top2_chunk builds a balanced tree (depth 4) over 32 registers with them; the
+// serial form is a 16-deep dependent chain of VIMNMX3.
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
-__device__ __forceinline__ int max_tree32(const int* v) {
-  int t[11];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) t[i] = imax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-  t[10] = max(v[30], v[31]);
-  const int u0 = imax3(t[0], t[1], t[2]), u1 = imax3(t[3], t[4], t[5]), u2 = imax3(t[6], t[7], t[8]);
-  return max(imax3(u0, u1, u2), max(t[9], t[10]));
-}
-__device__ __forceinline__ int min_tree32(const int* v) {
-  int t[11];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) t[i] = imin3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-  t[10] = min(v[30], v[31]);
-  const int u0 = imin3(t[0], t[1], t[2]), u1 = imin3(t[3], t[4], t[5]), u2 = imin3(t[6], t[7], t[8]);
-  return min(imin3(u0, u1, u2), min(t[9], t[10]));
-}
-
 // Running top-2 of one query row as two 64-bit keys (d << 32 | original index), d = d2 - |q|^2:
 // signed 64-bit order is the (distance, index) lexicographic order.
 struct Top2 {
@@ -198,6 +177,7 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
   }
 }
 
+template <bool kShare>  // kShare: query rows are swept by several units that share their thresholds
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_db, const MatchArgs a) {
@@ -245,8 +225,6 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * kBlockQ; i += kThreads)  // threshold exchange slots: tag 0 = unused
-    reinterpret_cast<long long*>(smem + kOffThr)[i] = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -345,18 +323,14 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
       Top2 best{kNoKey64, kNoKey64, kNoKey};
-#if SOD_EPI_MODE != 1 && SOD_SHARE_THR
-      // The row's other thread (other tile parity / column half) publishes its 2nd best here, tagged
-      // with the unit counter so a value from another unit (= another query row) is never used.
-      // 8-byte shared-memory accesses are single instructions; a stale value only prunes less.
-      volatile long long* thr_mine =
-          reinterpret_cast<volatile long long*>(smem + kOffThr) + par * kBlockQ + (row - qb * kBlockQ);
-      volatile long long* thr_other =
-          reinterpret_cast<volatile long long*>(smem + kOffThr) + (par ^ 1u) * kBlockQ + (row - qb * kBlockQ);
-      const long long tag = static_cast<long long>(ucount) << 32;
+      // Threshold sharing between the units that sweep different database segments for the same
+      // query rows (and between the row's two threads): every holder of the row publishes its 2nd
+      // best with atomicMin, everyone prunes with the minimum.  Any unit's 2nd best is an upper
+      // bound of the row's final 2nd best, so this stays exact; without it every segment pays the
+      // ~2 ln(n) threshold-establishing updates again.
+      int* const gthr = kShare ? a.row_thr + (qb * kBlockQ + h * kTileM + quad * 32 + lane) : nullptr;
       int published = kNoKey;
-#endif
-      int thr = kNoKey;
+      int thr = kShare ? min(kNoKey, __ldcg(gthr)) : kNoKey;
       for (int t = t0; t < t1; ++t, ++step) {
 #if SOD_EPI_MODE == 2
         if ((step & 1u) != par) continue;
@@ -370,12 +344,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         const int32_t* cs = reinterpret_cast<const int32_t*>(smem + kOffCq + slot * kCqTileBytes);
         const int32_t* perm_s = cs + kCqPerm;
-#if SOD_EPI_MODE != 1 && SOD_SHARE_THR
-        {
-          const long long o = *thr_other;
-          if ((o >> 32) == (tag >> 32)) thr = min(thr, static_cast<int>(o));
-        }
-#endif
+        // fetched now, folded in after this tile: the L2 round trip hides behind the tile's work
+        const int g_next = kShare ? __ldcg(gthr) : kNoKey;
 #if SOD_EPI_MODE == 1
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
         const int4* c4 = reinterpret_cast<const int4*>(cs);
@@ -440,12 +410,13 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
         top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
 #endif
-#if SOD_EPI_MODE != 1 && SOD_SHARE_THR
-        if (best.d2 < published) {
-          published = best.d2;
-          *thr_mine = tag | static_cast<unsigned>(published);
+        if (kShare) {
+          if (best.d2 < published) {
+            published = best.d2;
+            atomicMin(gthr, published);
+          }
+          thr = min(thr, g_next);
         }
-#endif
       }
       if (row < a.nq) {
         const int qn = a.qn[row];
@@ -660,8 +631,9 @@ Plan make_plan(int64_t nq, int64_t ndb, int sms) {
     for (int s = 1; s <= max_seg; ++s) {
       const int64_t units = static_cast<int64_t>(p.n_qblocks) * s;
       const int64_t waves = (units + sms - 1) / sms;
-      // +24: a unit restarts the pruning threshold, its first ~2k columns run the slow path
-      const int64_t cost = waves * ((p.n_tiles + s - 1) / s + 24);
+      // +12: pipeline fill and the slow-path chunks of a unit's first columns (measured; units of one
+      // query block share their thresholds, so a later segment does not start from scratch)
+      const int64_t cost = waves * ((p.n_tiles + s - 1) / s + 12);
       if (best < 0 || cost < best) {
         best = cost;
         p.n_seg = s;
@@ -750,11 +722,19 @@ int sod_query_prepare(const uint8_t* q, int64_t n_rows, int32_t* qn, sod_stream_
   return SOD_OK;
 }
 
+// partial lists [n_seg * kParity][nq][2] (d2 + idx), then the shared thresholds [n_qblocks * 256]
+static size_t match_lists_bytes(const Plan& p, int64_t n_query) {
+  return static_cast<size_t>(p.n_seg) * kParity * static_cast<size_t>(n_query) * 2 * 8;
+}
+static size_t match_workspace_need(const Plan& p, int64_t n_query) {
+  return match_lists_bytes(p, n_query) + static_cast<size_t>(p.n_qblocks) * kBlockQ * 4;
+}
+
 size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db) {
   if (n_query <= 0 || n_db <= 0) return 16;
   const int sms = device_sm_count();
   const Plan p = make_plan(n_query, n_db, sms > 0 ? sms : 148);
-  return static_cast<size_t>(p.n_seg) * kParity * static_cast<size_t>(n_query) * 2 * 8 + 16;
+  return match_workspace_need(p, n_query) + 16;
 }
 
 int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
@@ -785,7 +765,7 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   const int sms = device_sm_count();
   if (sms <= 0) return SOD_ERR_CUDA;
   const Plan p = make_plan(n_query, n_db, sms);
-  const size_t need = static_cast<size_t>(p.n_seg) * kParity * static_cast<size_t>(n_query) * 2 * 8;
+  const size_t need = match_workspace_need(p, n_query);
   SOD_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
 
   CUtensorMap map_q, map_db;
@@ -799,6 +779,12 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   a.cq = cq;
   a.part_d2 = static_cast<uint32_t*>(workspace);
   a.part_idx = reinterpret_cast<int32_t*>(a.part_d2 + static_cast<size_t>(p.n_seg) * kParity * n_query * 2);
+  // Thresholds are shared whenever a query row is swept by more than one unit; 0x7F7F7F7F = none yet
+  a.row_thr = nullptr;
+  if (p.n_seg > 1) {
+    a.row_thr = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + match_lists_bytes(p, n_query));
+    SOD_CHECK_CUDA(cudaMemsetAsync(a.row_thr, 0x7F, static_cast<size_t>(p.n_qblocks) * kBlockQ * 4, st));
+  }
   a.nq = static_cast<int>(n_query);
   a.n_tiles = p.n_tiles;
   a.n_qblocks = p.n_qblocks;
@@ -807,11 +793,16 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
 
   static bool attr_set = false;
   if (!attr_set) {
-    SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytes));
+    SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
     attr_set = true;
   }
-  match_top2_kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
+  if (a.row_thr)
+    match_top2_kernel<true><<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
+  else
+    match_top2_kernel<false><<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
   SOD_CHECK_LAUNCH("match_top2_kernel");
   top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(a.part_idx, a.part_d2, p.n_seg * kParity, n_query,
                                                   out_idx, out_d2, nullptr, nullptr, 0.0);
