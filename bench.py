@@ -344,7 +344,10 @@ def run_ours(args):
         except Exception:
             pass
         bf16_sus = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak = 2.0 * bf16_sus
+        # MEASURED_PEAKS.json has no int8 entry.  int8 dense is nominally 2 x bf16 dense, and the
+        # cuBLASLt int8 GEMM probe of this very run is a second measured ceiling: the denominator is
+        # the LARGER of the two, so that the fraction never flatters the kernel.
+        peak = max(2.0 * bf16_sus, int8_tops or 0.0)
         shard_rows = pipe.row_hi - pipe.row_lo
         ops = 2.0 * nq * shard_rows * 128
         achieved = ops / (match_ms * 1e-3) / 1e12
@@ -368,8 +371,9 @@ def run_ours(args):
                          "algorithmic": {"ops": ops, "definition": "2 * n_query * n_db_shard * 128 int8 ops per launch",
                                          "min_bytes": nq * 128 + shard_rows * 128},
                          "kernel_ms": match_ms,
-                         "peak_source": ("2 x MEASURED_PEAKS.bf16_tflops_sustained (int8 dense = 2 x bf16 dense on B200; "
-                                         "no measured int8 entry)" if peaks else "2 x 1400 TFLOP/s fallback"),
+                         "peak_source": ("max(2 x MEASURED_PEAKS.bf16_tflops_sustained = %.1f, cuBLASLt int8 8192^3 GEMM "
+                                         "measured in this run = %.1f); MEASURED_PEAKS.json has no int8 entry%s"
+                                         % (2.0 * bf16_sus, int8_tops or 0.0, "" if peaks else " (file absent: 1400 fallback)")),
                          "frac_of_nominal_int8_4500": achieved / 4500.0,
                          "int8_cublaslt_8192_tops": int8_tops},
             "result_check": {"matches": res["n_matches"], "bins": res["n_bins"], "valid_bins": res["n_valid"],
