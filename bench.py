@@ -119,14 +119,37 @@ def make_workload(args, device):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU DURING the timed region: an NVML polling thread
+    (2 ms period, so even an 8-GPU step of ~15 ms is sampled); `nvidia-smi -lms` as fallback."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.nvml, self.handle, self.samples, self.mask, self.max_mhz = None, None, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, handle
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -134,11 +157,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            n = self.nvml
+            flags = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap,
+                     "hw_power_brake": n.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, v in flags.items() if self.mask & v), "samples": len(self.samples),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -157,7 +202,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
