@@ -30,18 +30,6 @@
 #include "sod_ptx.cuh"
 #include "sod_tma.cuh"
 
-// Epilogue organisation (compile-time experiment switch; all three give identical results):
-//   1 = 8 warps: (lane quadrant x query half), 128 columns per tile, slot released right after the load
-//   2 = 16 warps: as 1 but split by tile parity (every other tile each), two 64-column loads
-//   3 = 16 warps: split by column half (64 columns of every tile each)
-//   4 = 24 warps: 3-way tile interleave (every third tile each), four 32-column loads
-#ifndef SOD_EPI_MODE
-#define SOD_EPI_MODE 2
-#endif
-#ifndef SOD_EXP
-#define SOD_EXP 0  // kernel experiments (timing only, results invalid): 1 = no epilogue math, 2 = no TMEM loads
-#endif
-
 namespace sod {
 namespace {
 
@@ -51,20 +39,20 @@ constexpr int kBlockQ = kTileM * kHalves;   // 256 query rows per unit
 constexpr int kTileN = SOD_TILE_ROWS;       // database rows per MMA
 constexpr int kTileBytes = kTileN * SOD_DESC_DIM;  // 16 KB (A half-tile has the same size)
 constexpr int kStages = 6;
-constexpr int kCqSlots = kStages + 6;       // see the slot-reuse argument in the producer (12 covers
-                                            // up to a 3-way tile interleave of the epilogue warps)
+constexpr int kCqSlots = kStages + 6;       // see the slot-reuse argument in the producer
 constexpr int kChunk = 32;                  // accumulator columns per tcgen05.ld
 constexpr int kCqTile = SOD_CQ_TILE_INTS;   // 128 x |t|^2 + 4 per-chunk minima + 128 x original row
 constexpr int kCqPerm = kTileN + 4;         // offset of the permutation inside a tile's slice
 constexpr int kCqTileBytes = kCqTile * 4;   // 1040 B, a multiple of 16 for the bulk copy
 constexpr int kNoKey = 0x7FFFFF;            // |t|^2 of padding rows / "no candidate yet" (> 128*255^2,
                                             // and (kNoKey << 8 | 127) still fits int32)
-constexpr int kParity = SOD_EPI_MODE == 1 ? 1 : SOD_EPI_MODE == 4 ? 3 : 2;  // candidate lists per row and segment
-constexpr int kEpiWarps = 4 * kHalves * kParity;    // (TMEM lane quadrant) x (query half) x (split)
+constexpr int kParity = 2;                  // epilogue warps per (quadrant, half): even / odd tiles; one
+                                            // candidate list per row, segment and parity
+constexpr int kEpiWarps = 4 * kHalves * kParity;    // (TMEM lane quadrant) x (query half) x (tile parity)
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kRegsLight = 56;      // producer / MMA / allocator warpgroup after setmaxnreg.dec
-constexpr int kRegsEpilogue = SOD_EPI_MODE == 1 ? 224 : SOD_EPI_MODE == 4 ? 72 : 104;  // accumulators + keys + state
+constexpr int kRegsEpilogue = 104;  // 64 accumulators + keys + state
 // setmaxnreg only moves registers inside the CTA's launch allocation (threads x launch registers,
 // the latter a multiple of 8): asking for more makes setmaxnreg.inc wait forever.
 constexpr int kRegsLaunch = 65536 / kThreads / 8 * 8;
@@ -75,10 +63,9 @@ constexpr int kOffA = 0;                                    // [2 buffers][2 hal
 constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;     // [kStages][16 KB]
 constexpr int kOffCq = kOffB + kStages * kTileBytes;        // [kCqSlots][128] int32
 constexpr int kOffBar = kOffCq + kCqSlots * kCqTileBytes;
-constexpr int kBarGroups = SOD_EPI_MODE == 4 ? 3 : 2;  // accumulator barriers are indexed by step % kBarGroups:
-                                                       // every barrier is then waited on by ONE set of epilogue
-                                                       // warps for consecutive phases (a parity wait must never
-                                                       // skip a phase)
+constexpr int kBarGroups = kParity;  // accumulator barriers are indexed by step % kBarGroups: every barrier is
+                                     // then waited on by ONE set of epilogue warps for consecutive phases (a
+                                     // parity wait must never skip a phase)
 constexpr int kNumBars = 2 * kStages + 4 + 4 * kBarGroups + kCqSlots;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // +1024: manual 1 KB alignment
@@ -97,10 +84,9 @@ struct MatchArgs {
   int idx_base;
 };
 
-// 3-input min / max: top2_chunk builds a balanced tree (depth 4) over 32 registers with them; the
+// 3-input max: top2_chunk builds a balanced tree (depth 4) over 32 registers with them; the
 // serial form is a 16-deep dependent chain of VIMNMX3.
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
-__device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
 // Running top-2 of one query row as two 64-bit keys (d << 32 | original index), d = d2 - |q|^2:
 // signed 64-bit order is the (distance, index) lexicographic order.
 struct Top2 {
@@ -137,9 +123,6 @@ constexpr long long kNoKey64 = (static_cast<long long>(kNoKey) << 32) | 0x7FFFFF
 __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __restrict__ cp4,
                                            int cmin, const int32_t* __restrict__ perm_s,
                                            int idx_base, Top2& best, int& thr) {
-#if SOD_EXP == 1 || SOD_EXP == 2
-  return;
-#endif
   // level 1, with the sub-tree maxima of the balanced tree kept: elements 0-8, 9-17, 18-26, 27-31
   const int* av = reinterpret_cast<const int*>(v);
   int t[11];
@@ -216,7 +199,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int g = 0; g < kBarGroups; ++g)
       for (int h = 0; h < kHalves; ++h) {
         mbar_init(bar_tfull(g, h), 1);
-        mbar_init(bar_tempty(g, h), SOD_EPI_MODE == 3 ? 8 : 4);  // warps that read one slot
+        mbar_init(bar_tempty(g, h), 4);  // the four quadrant warps that read one slot
       }
     for (int s = 0; s < kCqSlots; ++s) mbar_init(bar_cqfull(s), 1);
     fence_mbar_init();
@@ -313,7 +296,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int e = warp - 4;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int h = (e >> 2) & 1;         // which query half-tile
-    const uint32_t par = e >> 3;        // which tiles (modes 2, 4) or which 64-column half (mode 3)
+    const uint32_t par = e >> 3;        // this warp takes the tiles with (step & 1) == par
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t step = 0, ucount = 1;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
@@ -332,11 +315,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int published = kNoKey;
       int thr = kShare ? min(kNoKey, __ldcg(gthr)) : kNoKey;
       for (int t = t0; t < t1; ++t, ++step) {
-#if SOD_EPI_MODE == 2
         if ((step & 1u) != par) continue;
-#elif SOD_EPI_MODE == 4
-        if (step % 3u != par) continue;
-#endif
         const uint32_t acc = step & 1u, bg = step % kBarGroups, bgph = (step / kBarGroups) & 1u;
         const uint32_t slot = step % kCqSlots, cqph = (step / kCqSlots) & 1u;
         mbar_wait(bar_cqfull(slot), cqph);  // landed long ago: returns at the first poll
@@ -346,70 +325,19 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int32_t* perm_s = cs + kCqPerm;
         // fetched now, folded in after this tile: the L2 round trip hides behind the tile's work
         const int g_next = kShare ? __ldcg(gthr) : kNoKey;
-#if SOD_EPI_MODE == 1
-        const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
-        const int4* c4 = reinterpret_cast<const int4*>(cs);
-        const int4 cmin = c4[kTileN / 4];
-        uint32_t v[kTileN];
-#if SOD_EXP != 2
-        tmem_ld128_wait(taddr, v);
-#endif
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
-        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
-        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
-        top2_chunk(v + 2 * kChunk, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
-        top2_chunk(v + 3 * kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
-#elif SOD_EPI_MODE == 2
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
         const int4* c4 = reinterpret_cast<const int4*>(cs);
         const int4 cmin = c4[kTileN / 4];
         uint32_t v[2 * kChunk];
-#if SOD_EXP != 2
         tmem_ld64_wait(taddr, v);
-#endif
         top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
         top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
-#if SOD_EXP != 2
         tmem_ld64_wait(taddr + 2 * kChunk, v);
-#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(bg, h));
         top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
         top2_chunk(v + kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
-#elif SOD_EPI_MODE == 4
-        const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
-        const int4* c4 = reinterpret_cast<const int4*>(cs);
-        const int4 cmin = c4[kTileN / 4];
-        uint32_t v[kChunk];
-        tmem_ld32_wait(taddr, v);
-        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
-        tmem_ld32_wait(taddr + kChunk, v);
-        top2_chunk(v, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
-        tmem_ld32_wait(taddr + 2 * kChunk, v);
-        top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
-        tmem_ld32_wait(taddr + 3 * kChunk, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
-        top2_chunk(v, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
-#else
-        const uint32_t taddr =
-            tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN + par * (2 * kChunk);
-        uint32_t v[2 * kChunk];
-#if SOD_EXP != 2
-        tmem_ld64_wait(taddr, v);
-#endif
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
-        const int4* c4 = reinterpret_cast<const int4*>(cs) + par * 16;
-        const int2 cmin = *reinterpret_cast<const int2*>(cs + kTileN + par * 2);
-        top2_chunk(v, c4, cmin.x, perm_s, a.idx_base, best, thr);
-        top2_chunk(v + kChunk, c4 + 8, cmin.y, perm_s, a.idx_base, best, thr);
-#endif
         if (kShare) {
           if (best.d2 < published) {
             published = best.d2;
