@@ -682,12 +682,8 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
   const size_t hist_bytes = static_cast<size_t>(bins) * bins * bins * bins * sizeof(uint32_t);
-  static size_t attr_bytes = 0;
-  if (hist_bytes > attr_bytes) {
-    SOD_CHECK_CUDA(cudaFuncSetAttribute(hough_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(hist_bytes)));
-    attr_bytes = hist_bytes;
-  }
+  SOD_CHECK_CUDA(cudaFuncSetAttribute(hough_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(hist_bytes)));  // per device, hence at every launch
   int64_t group_chunk = n_groups / (static_cast<int64_t>(sms) * 8);
   group_chunk = group_chunk < 1 ? 1 : (group_chunk > kGroupChunk ? kGroupChunk : group_chunk);
   va.group_chunk = static_cast<int>(group_chunk);

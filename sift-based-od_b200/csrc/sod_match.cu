@@ -719,18 +719,10 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   a.n_seg = p.n_seg;
   a.idx_base = db_index_base;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
-    SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
-    attr_set = true;
-  }
-  if (a.row_thr)
-    match_top2_kernel<true><<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
-  else
-    match_top2_kernel<false><<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
+  // The attribute is per device (a process may drive several), so it is set at every launch: ~1 us.
+  auto* kernel = a.row_thr ? match_top2_kernel<true> : match_top2_kernel<false>;
+  SOD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
   SOD_CHECK_LAUNCH("match_top2_kernel");
   top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(a.part_idx, a.part_d2, p.n_seg * kParity, n_query,
                                                   out_idx, out_d2, nullptr, nullptr, 0.0);

@@ -433,12 +433,8 @@ int sod_match_top2_bf16(const uint16_t* q_op, const float* qn, int64_t n_query, 
   a.k_blocks = k_blocks;
   a.idx_base = db_index_base;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        smem_bytes(kMaxKBlocks)));
-    attr_set = true;
-  }
+  SOD_CHECK_CUDA(cudaFuncSetAttribute(match_top2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_bytes(kMaxKBlocks)));  // per device, hence at every launch
   const dim3 grid(static_cast<unsigned>(p.n_qblocks), static_cast<unsigned>(p.n_seg));
   match_top2_bf16_kernel<<<grid, kThreads, smem_bytes(k_blocks), st>>>(map_q, map_db, a);
   SOD_CHECK_LAUNCH("match_top2_bf16_kernel");

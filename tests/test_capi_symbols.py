@@ -43,6 +43,27 @@ def test_error_reporting_without_gpu():
     assert lib.sod_compact_scratch_bytes(5000) >= 8 * 6
 
 
+def test_argument_checks_of_the_newer_entry_points_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on the CPU."""
+    from sod_b200 import _capi
+    lib = _capi.lib
+    assert lib.sod_bf16_operand_cols(0) == 128 and lib.sod_bf16_operand_cols(1) == 384
+    assert lib.sod_bf16_db_rows(0) == 0 and lib.sod_bf16_db_rows(1) == 128 and lib.sod_bf16_db_rows(129) == 256
+    assert lib.sod_bf16_prepare(None, 4, 2, 1, None, None, None, None) == -1 and b"side" in lib.sod_last_error()
+    assert lib.sod_bf16_prepare(None, 4, 0, 1, None, None, None, None) == -1 and b"null" in lib.sod_last_error()
+    assert lib.sod_bf16_prepare(None, 0, 0, 1, None, None, None, None) == 0          # nothing to do
+    assert lib.sod_match_top2_bf16(None, None, -1, None, None, 0, 1, 0, None, None, None, 0, None) == -1
+    assert lib.sod_match_top2(None, None, 3, None, None, 2 ** 31, 0, None, None, None, 0, None) == -1
+    assert b"out of range" in lib.sod_last_error()
+    assert lib.sod_match_top2(None, None, 3, None, None, 5, 2 ** 31 - 3, None, None, None, 0, None) == -1
+    assert b"overflows" in lib.sod_last_error()
+    assert lib.sod_top2_merge_f32(None, None, 2, 10, None, None, None, None, 0.75, None) == -1
+    assert lib.sod_pose_adjacency(None, None, None, None, None, 65537, None, None, None) == -1
+    assert b"65536" in lib.sod_last_error()
+    assert lib.sod_angle_adjacency(None, None, 10, 1.0, None, None, None) == -1 and b"null" in lib.sod_last_error()
+    assert lib.sod_pose_adjacency(None, None, None, None, None, 0, None, None, None) == 0
+
+
 def test_product_does_not_import_the_oracle():
     pkg = ROOT / "sift-based-od_b200"
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
