@@ -146,7 +146,9 @@ __global__ void pose_bin_index_kernel(const double* __restrict__ pose, int64_t n
                 (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
 }
 
-// Exclusive scan of n ints by one CTA (n is the number of Hough spaces: small).
+// Exclusive scan of n ints by one CTA, 8 consecutive elements per thread and round (n is the number
+// of Hough spaces or of compaction blocks: up to a few 100k, i.e. a few dozen rounds).
+constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ in,
                                                               int64_t n, int32_t* __restrict__ out,
                                                               int32_t* __restrict__ out_copy,
@@ -156,10 +158,16 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int64_t base = 0; base < n; base += blockDim.x) {
-    const int64_t i = base + threadIdx.x;
-    const int32_t v = i < n ? in[i] : 0;
-    int32_t incl = v;
+  for (int64_t base = 0; base < n; base += static_cast<int64_t>(blockDim.x) * kScanItems) {
+    const int64_t i0 = base + static_cast<int64_t>(threadIdx.x) * kScanItems;
+    int32_t v[kScanItems];
+    int32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      v[k] = i0 + k < n ? in[i0 + k] : 0;
+      sum += v[k];
+    }
+    int32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -177,10 +185,14 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
       warp_sums[lane] = w;
     }
     __syncthreads();
-    const int32_t excl = carry + (warp ? warp_sums[warp - 1] : 0) + incl - v;
-    if (i < n) {
-      out[i] = excl;
-      if (out_copy) out_copy[i] = excl;
+    int32_t excl = carry + (warp ? warp_sums[warp - 1] : 0) + incl - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (i0 + k < n) {
+        out[i0 + k] = excl;
+        if (out_copy) out_copy[i0 + k] = excl;
+      }
+      excl += v[k];
     }
     __syncthreads();
     if (threadIdx.x == 0) carry += warp_sums[31];
