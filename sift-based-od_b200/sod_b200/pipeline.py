@@ -79,27 +79,57 @@ class DetectionPipeline:
             groups_per_frame=n_images if per_object_spaces else 1, device=dev)
         self.voter = E.HoughVoter(self.scene, bins)
         self._aff: E.AffineResult | None = None
+        # two sets of query-side buffers: set 0 is the one allocated above; set 1 appears on first use
+        self._qsets = [dict(des=self.q_des, xy=self.scene.q_xy, angle=self.scene.q_angle,
+                            octave=self.scene.q_octave, frame=self.scene.q_frame), None]
+        self._copy_stream = None
+        self._loaded = [None, None]      # event: the set's host->device copies have landed
+        self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
         if world > 1:
             self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
             self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
         self.launches_per_call = 16  # our kernels per detect_device call
 
     # ---------------------------------------------------------------- device-resident inputs
-    def load_queries(self, des, xy, angle, octave, frame) -> int:
-        """Copy one batch of query frames (host or device arrays) into the pipeline's buffers."""
+    def _qset(self, slot: int) -> dict:
+        if self._qsets[slot] is None:
+            self._qsets[slot] = {k: torch.empty_like(v) for k, v in self._qsets[0].items()}
+        return self._qsets[slot]
+
+    def load_queries(self, des, xy, angle, octave, frame, slot: int = 0, overlap: bool = False) -> int:
+        """Copy one batch of query frames (host or device arrays) into query-buffer set `slot`.
+        overlap=True issues the copies on the pipeline's copy stream, so that (with pinned host
+        memory) they run while the kernels of the other set are busy; detect_device(n, slot) waits
+        for them on the device."""
         n = int(des.shape[0])
         if n > self.max_queries:
             raise ValueError("batch larger than max_queries")
         t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(a)  # noqa: E731
-        self.q_des[:n].copy_(t(des), non_blocking=True)
-        self.scene.q_xy[:n].copy_(t(xy), non_blocking=True)
-        self.scene.q_angle[:n].copy_(t(angle), non_blocking=True)
-        self.scene.q_octave[:n].copy_(t(octave), non_blocking=True)
-        self.scene.q_frame[:n].copy_(t(frame), non_blocking=True)
+        q = self._qset(slot)
+        if overlap and self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        stream = self._copy_stream if overlap else torch.cuda.current_stream(self.device)
+        if overlap:
+            stream.wait_stream(torch.cuda.current_stream(self.device)) if self._consumed[slot] is None else \
+                stream.wait_event(self._consumed[slot])
+        with torch.cuda.stream(stream):
+            for key, src in (("des", des), ("xy", xy), ("angle", angle), ("octave", octave), ("frame", frame)):
+                q[key][:n].copy_(t(src), non_blocking=True)
+            if overlap:
+                self._loaded[slot] = torch.cuda.Event()
+                self._loaded[slot].record(stream)
+        if not overlap:
+            self._loaded[slot] = None
         return n
 
-    def detect_device(self, n: int):
-        """Run the path on the first n loaded query rows; everything stays on the device."""
+    def detect_device(self, n: int, slot: int = 0):
+        """Run the path on the first n rows of query-buffer set `slot`; everything stays on the device."""
+        qs = self._qset(slot)
+        if self._loaded[slot] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._loaded[slot])
+        sc = self.scene
+        self.q_des, sc.q_xy, sc.q_angle, sc.q_octave, sc.q_frame = (qs["des"], qs["xy"], qs["angle"], qs["octave"],
+                                                                    qs["frame"])
         q = self.q_des[:n]
         idx, d2 = self.matcher.top2(q)
         if self.world > 1:
@@ -123,6 +153,8 @@ class DetectionPipeline:
             self._aff = E.AffineResult(hough, self.vote_threshold, self.device)
         aff = E.affine_verify(self.scene, mq, mt, hough, self.vote_threshold, self.affine_threshold,
                               result=self._aff)
+        self._consumed[slot] = torch.cuda.Event()
+        self._consumed[slot].record()
         return dict(idx=idx, d2=d2, dist=dist_f, ok=ok, match_q=mq, match_t=mt, n_matches=n_dev,
                     hough=hough, affine=aff)
 
@@ -132,6 +164,23 @@ class DetectionPipeline:
         n = self.load_queries(des, xy, angle, octave, frame)
         r = self.detect_device(n)
         return self.fetch(r)
+
+    def detect_batches(self, batches):
+        """Host batches in, host results out, with the host->device copy of batch i+1 overlapping the
+        kernels of batch i (two query-buffer sets, one copy stream).  `batches` yields
+        (des, xy, angle, octave, frame) tuples of pinned host arrays; results are yielded in order."""
+        it = iter(batches)
+        nxt = next(it, None)
+        slot = 0
+        if nxt is not None:
+            n_next = self.load_queries(*nxt, slot=slot, overlap=True)
+        while nxt is not None:
+            r = self.detect_device(n_next, slot)
+            nxt = next(it, None)
+            if nxt is not None:
+                n_next = self.load_queries(*nxt, slot=slot ^ 1, overlap=True)
+            yield self.fetch(r)
+            slot ^= 1
 
     def fetch(self, r: dict) -> dict:
         """Device -> host read of one result: matches, counters, verified bins of this rank."""

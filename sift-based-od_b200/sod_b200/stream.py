@@ -142,15 +142,14 @@ class FrameStream:
         return self._staging[slot].fill(feats)
 
     def _enqueue(self, slot: int, n: int):
-        """Host->device copies and the kernels of one staged batch, all asynchronous."""
-        import torch
+        """Host->device copies (on the pipeline's copy stream, so they overlap the kernels of the
+        previous batch) and the kernels of one staged batch, all asynchronous."""
         p, st = self.pipeline, self._staging[slot]
         p.scene.frame_wh[:self.batch_frames].copy_(st.frame_wh, non_blocking=True)
-        p.load_queries(st.des[:n], st.xy[:n], st.angle[:n], st.octave[:n], st.frame[:n])
-        if self._on_gpu:
-            self._copied[slot] = torch.cuda.Event()
-            self._copied[slot].record()
-        return p.detect_device(n)
+        p.load_queries(st.des[:n], st.xy[:n], st.angle[:n], st.octave[:n], st.frame[:n], slot=slot,
+                       overlap=self._on_gpu)
+        self._copied[slot] = getattr(p, "_loaded", [None, None])[slot]
+        return p.detect_device(n, slot)
 
     def _finish(self, r, feats: list[FrameFeatures], first_index: int):
         """Device->host read of a batch (synchronises) + final poses, split per frame."""

@@ -27,3 +27,37 @@ def test_pipeline_to_final_pose_equals_reference(name):
     got = np.array([[c[0], c[1], o, s, sh[0], sh[1]] for (c, o, s, sh) in poses.get(0, [])], np.float64).reshape(-1, 6)
     assert got.shape == z["final_pose"].shape
     np.testing.assert_allclose(got, z["final_pose"], rtol=1e-10, atol=1e-9)
+
+
+def test_overlapped_batches_equal_one_at_a_time():
+    """detect_batches (copy stream + two query-buffer sets) returns, batch by batch, exactly what
+    detect returns for the same batch; the batches differ so that a mixed-up buffer would show."""
+    import torch
+    import bench
+    from sod_b200.pipeline import DetectionPipeline, ModelDatabase
+    args = type("A", (), dict(objects=40, kp_per_object=400, frames=4, per_frame=1200, instances=3,
+                              inlier_frac=0.2, false_frac=0.02))()
+    dev = torch.device("cuda")
+    wl = bench.make_workload(args, dev)
+    db = ModelDatabase(wl["db_des"], wl["m_xy"], wl["m_angle"], wl["m_octave"], wl["m_image"],
+                       wl["img_centroid"], wl["img_size"])
+    nq = args.frames * args.per_frame
+    host = [torch.as_tensor(wl[k]).cpu() for k in ("q_des", "q_xy", "q_angle", "q_octave", "q_frame")]
+    batches = []
+    for shift in (0, 1, 2, 3, 4):           # rotate the query rows of each frame: different matches per batch
+        perm = torch.arange(nq).view(args.frames, -1).roll(shift * 37, 1).roll(shift, 0).reshape(-1)
+        b = [h[perm].contiguous().pin_memory() for h in host]
+        b[4] = host[4].clone().pin_memory()   # frame id stays positional
+        batches.append(tuple(b))
+    pipe = DetectionPipeline(db, nq, wl["frame_wh"], device=dev)
+    want = [pipe.detect(*b) for b in batches]
+    got = list(pipe.detect_batches(iter(batches)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g["n_matches"] == w["n_matches"] and g["n_valid"] == w["n_valid"] and w["n_valid"] > 0
+        np.testing.assert_array_equal(g["idx"], w["idx"])
+        np.testing.assert_array_equal(g["ok"], w["ok"])
+        og, ow = (np.lexsort((x["valid_code"], x["valid_group"])) for x in (g, w))   # compaction order is free
+        for k in ("valid_group", "valid_code", "votes", "status", "params"):
+            np.testing.assert_array_equal(g[k][og], w[k][ow])
+    assert not np.array_equal(want[0]["idx"], want[1]["idx"])

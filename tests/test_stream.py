@@ -28,11 +28,11 @@ class _EchoPipeline:
         self.max_queries, self.scene = max_queries, _Scene(n_frames)
         self.calls = []
 
-    def load_queries(self, des, xy, angle, octave, frame):
+    def load_queries(self, des, xy, angle, octave, frame, slot=0, overlap=False):
         self._q = (des.clone(), frame.clone())
         return des.shape[0]
 
-    def detect_device(self, n):
+    def detect_device(self, n, slot=0):
         des, frame = self._q
         self.calls.append((n, self.scene.frame_wh.clone()))
         return dict(des=des[:n], frame=frame[:n])
