@@ -4,8 +4,9 @@ The reference handles one image per process run: Main.get_query_features (main.p
 runs OpenCV SIFT, and the matcher starts when that is done.  For a stream of frames the host-side
 SIFT is the slow stage, so FrameStream extracts features of upcoming frames on a pool of host
 threads (OpenCV releases the GIL) while the GPU runs match -> ratio -> Hough -> affine on the
-previous batch; batches are packed into pinned, double-buffered staging while the GPU is busy and
-handed to the caller while the next batch runs.  OpenCV SIFT itself stays the extractor (input
+previous batch; batches are packed into pinned, double-buffered staging while the GPU is busy, their
+host->device copies run on the pipeline's copy stream under the previous batch's kernels, and
+results are handed to the caller while the next batch runs.  OpenCV SIFT itself stays the extractor (input
 stage, out of scope for the GPU path).
 """
 from __future__ import annotations
