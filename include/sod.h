@@ -220,6 +220,16 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
                    const int32_t* sigma_lut, int32_t detail_min_count, const sod_hough_out* out,
                    void* workspace, size_t workspace_bytes, sod_stream_t stream);
 
+/* sod_hough_vote with one bin count per pose dimension, as the legacy perform_hough_transform takes
+ * them (HoughTransform.py:8: bin_x, bin_y, bin_theta, bin_sigma).  Bin codes are
+ * ((ix * bins_y + iy) * bins_theta + itheta) * bins_sigma + isigma; sigma_lut must be built for
+ * bins_sigma.  Each count <= 255 and their product <= SOD_MAX_BINS^4 (one SM's shared memory). */
+int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                        int64_t n_matches, const int32_t* n_matches_dev, int32_t bins_x, int32_t bins_y,
+                        int32_t bins_theta, int32_t bins_sigma, const int32_t* sigma_lut,
+                        int32_t detail_min_count, const sod_hough_out* out, void* workspace,
+                        size_t workspace_bytes, sod_stream_t stream);
+
 /* Outputs of sod_affine_verify (device), one entry per bin that entered with >= vote_threshold. */
 typedef struct {
   int32_t* counters;    /* [2] n_valid, overflow; zeroed by the call */

@@ -148,16 +148,25 @@ def estimate_pose(m_pt, m_angle, m_octave, q_pt, q_angle, q_octave, m_centroid):
     return (rx + q_pt[0], ry + q_pt[1], a, s)                 # :34-36
 
 
-def bin_index(pose, bins: int, img_h, img_w):
+def _bins4(bins):
+    return tuple(int(b) for b in bins) if isinstance(bins, (tuple, list)) else (int(bins),) * 4
+
+
+def bin_index(pose, bins, img_h, img_w):
     """Base bin of a pose (HoughTransformHelperFunctions.py:39-72): x,y truncate toward zero then
-    shift by -1 and clamp; theta modulo; log2 scale over 6.5 octaves, clamped."""
+    shift by -1 and clamp; theta modulo; log2 scale over 6.5 octaves, clamped.
+    bins may be (bin_x, bin_y, bin_theta, bin_sigma): the same expressions with the count of each
+    dimension, as the legacy perform_hough_transform writes them (HoughTransform.py:37-56).  The
+    reference cannot run that function (it raises on its first vote), so unequal counts
+    are parity-unpinned; equal counts are pinned by the golden fixtures."""
+    bx, by, bt, bs = _bins4(bins)
     x, y, theta, s = pose
-    ix = min(max(0, int((x * bins) / img_w) - 1), bins - 1)          # :49-52
-    iy = min(max(0, int((y * bins) / img_h) - 1), bins - 1)          # :55-58
-    it = int((theta * bins / (2 * math.pi)) % bins)                    # :61-63
+    ix = min(max(0, int((x * bx) / img_w) - 1), bx - 1)              # :49-52
+    iy = min(max(0, int((y * by) / img_h) - 1), by - 1)              # :55-58
+    it = int((theta * bt / (2 * math.pi)) % bt)                        # :61-63
     n_oct = 4
-    isg = int(math.log(s, 2) / (2 * (n_oct - 1) + 0.5) * bins)       # :66-67
-    isg = min(max(0, isg), bins - 1)                                   # :69-70
+    isg = int(math.log(s, 2) / (2 * (n_oct - 1) + 0.5) * bs)         # :66-67
+    isg = min(max(0, isg), bs - 1)                                     # :69-70
     return ix, iy, it, isg
 
 
@@ -228,11 +237,12 @@ class Scene:
                              (float(self.img_centroid[img, 0]), float(self.img_centroid[img, 1])))
 
 
-def hough_vote(scene: Scene, match_q, match_t, bins: int = 15):
+def hough_vote(scene: Scene, match_q, match_t, bins=15):
     """Main.apply_hough_transform (main.py:89-119): every match votes into the 2x2x2x2 bins starting
     at its base bin; candidates with any coordinate >= bins are dropped (no theta wrap).
     Returns an insertion-ordered dict (group, ix, iy, it, is) -> Bin."""
     table: dict = {}
+    b4 = _bins4(bins)
     for mid, (qi, ti) in enumerate(zip(match_q, match_t)):
         qi, ti = int(qi), int(ti)
         img = int(scene.m_image[ti])
@@ -245,7 +255,7 @@ def hough_vote(scene: Scene, match_q, match_t, bins: int = 15):
                 for y in range(2):
                     for z in range(2):
                         p = (ix + w, iy + x, it + y, isg + z)
-                        if p[0] < bins and p[1] < bins and p[2] < bins and p[3] < bins:   # :110
+                        if p[0] < b4[0] and p[1] < b4[1] and p[2] < b4[2] and p[3] < b4[3]:   # :110
                             key = (group,) + p
                             b = table.get(key)
                             if b is None:

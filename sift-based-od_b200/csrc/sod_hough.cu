@@ -22,7 +22,6 @@
 namespace sod {
 namespace {
 
-constexpr double kPi = 3.141592653589793;           // math.pi
 constexpr double kTwoPi = 2.0 * 3.141592653589793;  // 2*math.pi (exact doubling)
 constexpr double kDegToRad = 3.141592653589793 / 180.0;  // CPython's math.radians multiplier
 constexpr int kVoteThreads = 1024;
@@ -40,13 +39,22 @@ __device__ __forceinline__ bool near_integer(double f) {
   return fabs(f - r) <= 1e-9 * fmax(1.0, fabs(f));
 }
 
+// Bin counts of the four pose dimensions (x, y, theta, log2 scale).  The live path uses one count
+// for all four (main.py:89); the legacy perform_hough_transform takes them separately
+// (HoughTransform.py:8).  A bin code is ((cx * y + cy) * t + ct) * s + cs.
+struct Bins4 {
+  int x, y, t, s;
+  __host__ __device__ int total() const { return x * y * t * s; }
+  __host__ __device__ int code(int cx, int cy, int ct, int cs) const { return ((cx * y + cy) * t + ct) * s + cs; }
+};
+
 struct PoseArgs {
   sod_scene sc;
   const int32_t* match_q;
   const int32_t* match_t;
   const int32_t* n_dev;
   int64_t n_cap;
-  int bins;
+  Bins4 bins;
   const int32_t* sigma_lut;
   double* pose;
   uint32_t* base_bin;
@@ -64,7 +72,7 @@ __device__ __forceinline__ int64_t live_count(const int32_t* n_dev, int64_t cap)
 
 __global__ void hough_pose_kernel(const PoseArgs a) {
   const int64_t n = live_count(a.n_dev, a.n_cap);
-  const int bins = a.bins;
+  const Bins4 bins = a.bins;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int qi = a.match_q[i], ti = a.match_t[i];
@@ -92,15 +100,15 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
     double* po = a.pose + i * 4;
     po[0] = x; po[1] = y; po[2] = al; po[3] = s;
 
-    const double fx = __ddiv_rn(__dmul_rn(x, static_cast<double>(bins)), W);
-    const double fy = __ddiv_rn(__dmul_rn(y, static_cast<double>(bins)), H);
-    const double ft = fmod(__ddiv_rn(__dmul_rn(al, static_cast<double>(bins)), kTwoPi),
-                           static_cast<double>(bins));
+    const double fx = __ddiv_rn(__dmul_rn(x, static_cast<double>(bins.x)), W);
+    const double fy = __ddiv_rn(__dmul_rn(y, static_cast<double>(bins.y)), H);
+    const double ft = fmod(__ddiv_rn(__dmul_rn(al, static_cast<double>(bins.t)), kTwoPi),
+                           static_cast<double>(bins.t));
     // int() truncates toward zero; clamp before converting so huge poses stay defined
     int ix = static_cast<int>(fmin(fmax(trunc(fx), -1.0e6), 1.0e6));
     int iy = static_cast<int>(fmin(fmax(trunc(fy), -1.0e6), 1.0e6));
-    ix = min(max(0, ix - 1), bins - 1);
-    iy = min(max(0, iy - 1), bins - 1);
+    ix = min(max(0, ix - 1), bins.x - 1);
+    iy = min(max(0, iy - 1), bins.y - 1);
     const int it = static_cast<int>(ft);
     const int kk = min(max(k, SOD_SIGMA_LUT_MIN), SOD_SIGMA_LUT_MIN + SOD_SIGMA_LUT_LEN - 1);
     const int is = a.sigma_lut[kk - SOD_SIGMA_LUT_MIN];
@@ -219,7 +227,7 @@ struct VoteArgs {
   const uint32_t* base_bin;
   uint16_t* creator;         // per grouped position: which of the 16 votes created its bin
   int64_t n_groups;
-  int bins;
+  Bins4 bins;
   int group_chunk;           // Hough spaces per ticket: 1 for few large spaces ... kGroupChunk for many sparse ones
   int32_t* ticket;           // work-stealing counter over chunks of group_chunk Hough spaces (zeroed per call)
   int32_t* counters;
@@ -233,22 +241,21 @@ struct VoteArgs {
 
 // Calls f(o, code) for each of the <=16 in-range votes of a match (main.py:105-110).
 template <class F>
-__device__ __forceinline__ void for_each_vote(uint32_t base, int bins, F&& f) {
+__device__ __forceinline__ void for_each_vote(uint32_t base, const Bins4& bins, F&& f) {
   const int ix = base & 0xFF, iy = (base >> 8) & 0xFF, it = (base >> 16) & 0xFF, is = base >> 24;
 #pragma unroll
   for (int o = 0; o < 16; ++o) {
     const int cx = ix + ((o >> 3) & 1), cy = iy + ((o >> 2) & 1), ct = it + ((o >> 1) & 1),
               cs = is + (o & 1);
-    if (cx < bins && cy < bins && ct < bins && cs < bins)
-      f(o, ((cx * bins + cy) * bins + ct) * bins + cs);
+    if (cx < bins.x && cy < bins.y && ct < bins.t && cs < bins.s) f(o, bins.code(cx, cy, ct, cs));
   }
 }
 
 __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteArgs a) {
   extern __shared__ uint32_t hist[];  // bins^4 counters, all zero between groups
   __shared__ int s_nbins, s_nvotes, s_rec_base, s_vote_base, s_rec_cur, s_vote_cur, s_ok;
-  const int bins = a.bins;
-  const int nb4 = bins * bins * bins * bins;
+  const Bins4 bins = a.bins;
+  const int nb4 = bins.total();
   const int tid = threadIdx.x, lane = tid & 31;
   __shared__ int s_chunk, s_nlist;
   __shared__ int s_list[kGroupChunk];
@@ -360,7 +367,7 @@ struct FinishArgs {
   int64_t* bin_order;
   double* bin_mean;
   int64_t cap_bins;
-  int bins;
+  Bins4 bins;
   int detail_min_count;  // bins with fewer votes get no sorted members / means / order key
   int32_t* big_list;     // bins too large for one thread, finished by hough_finish_big_kernel
   int32_t* big_count;
@@ -372,10 +379,10 @@ constexpr int kSmallBin = 16;  // bins up to this size are finished by a single 
 __device__ __forceinline__ int64_t order_key(const FinishArgs& a, int64_t rec, int first) {
   const uint32_t base = a.base_bin[first];
   int code = a.bin_code[rec];
-  const int b = a.bins;
-  const int cs = code % b; code /= b;
-  const int ct = code % b; code /= b;
-  const int cy = code % b; code /= b;
+  const Bins4 b = a.bins;
+  const int cs = code % b.s; code /= b.s;
+  const int ct = code % b.t; code /= b.t;
+  const int cy = code % b.y; code /= b.y;
   const int cx = code;
   const int o = ((cx - static_cast<int>(base & 0xFF)) << 3) | ((cy - static_cast<int>((base >> 8) & 0xFF)) << 2) |
                 ((ct - static_cast<int>((base >> 16) & 0xFF)) << 1) | (cs - static_cast<int>(base >> 24));
@@ -607,7 +614,7 @@ int sod_estimate_pose(const sod_scene* scene, const int32_t* match_q, const int3
   PoseArgs pa;
   pa.sc = *scene;
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = nullptr; pa.n_cap = n_matches;
-  pa.bins = bins; pa.sigma_lut = sigma_lut; pa.pose = pose; pa.base_bin = base_bin;
+  pa.bins = Bins4{bins, bins, bins, bins}; pa.sigma_lut = sigma_lut; pa.pose = pose; pa.base_bin = base_bin;
   pa.near_edge = near_edge; pa.counters = nullptr; pa.group_of = nullptr; pa.group_count = nullptr;
   const int threads = 256;
   hough_pose_kernel<<<static_cast<unsigned>((n_matches + threads - 1) / threads), threads, 0,
@@ -639,11 +646,24 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
                    int64_t n_matches, const int32_t* n_matches_dev, int32_t bins,
                    const int32_t* sigma_lut, int32_t detail_min_count, const sod_hough_out* out,
                    void* workspace, size_t workspace_bytes, sod_stream_t stream) {
+  return sod_hough_vote_dims(scene, match_q, match_t, n_matches, n_matches_dev, bins, bins, bins, bins, sigma_lut,
+                             detail_min_count, out, workspace, workspace_bytes, stream);
+}
+
+int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const int32_t* match_t,
+                        int64_t n_matches, const int32_t* n_matches_dev, int32_t bins_x, int32_t bins_y,
+                        int32_t bins_theta, int32_t bins_sigma, const int32_t* sigma_lut,
+                        int32_t detail_min_count, const sod_hough_out* out, void* workspace,
+                        size_t workspace_bytes, sod_stream_t stream) {
   SOD_CHECK_ARG(scene && out, "null scene/out");
   SOD_CHECK_ARG(n_matches >= 0 && n_matches < (int64_t(1) << 27), "n_matches out of range");
-  SOD_CHECK_ARG(bins >= 1, "bins < 1");
-  if (bins > SOD_MAX_BINS) {
-    set_error("bins = %d: the shared-memory histogram holds at most %d^4 counters", bins, SOD_MAX_BINS);
+  SOD_CHECK_ARG(bins_x >= 1 && bins_y >= 1 && bins_theta >= 1 && bins_sigma >= 1, "bins < 1");
+  const Bins4 bins{bins_x, bins_y, bins_theta, bins_sigma};
+  constexpr int64_t kMaxCounters = int64_t(SOD_MAX_BINS) * SOD_MAX_BINS * SOD_MAX_BINS * SOD_MAX_BINS;
+  if (bins_x > 255 || bins_y > 255 || bins_theta > 255 || bins_sigma > 255 ||
+      int64_t(bins_x) * bins_y * bins_theta * bins_sigma > kMaxCounters) {
+    set_error("bins = %d x %d x %d x %d: the shared-memory histogram holds at most %d^4 counters", bins_x, bins_y,
+              bins_theta, bins_sigma, SOD_MAX_BINS);
     return SOD_ERR_UNSUPPORTED;
   }
   SOD_CHECK_ARG(out->counters, "null counters");
@@ -693,7 +713,7 @@ int sod_hough_vote(const sod_scene* scene, const int32_t* match_q, const int32_t
   va.n_groups = n_groups; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
-  const size_t hist_bytes = static_cast<size_t>(bins) * bins * bins * bins * sizeof(uint32_t);
+  const size_t hist_bytes = static_cast<size_t>(bins.total()) * sizeof(uint32_t);
   SOD_CHECK_CUDA(cudaFuncSetAttribute(hough_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(hist_bytes)));  // per device, hence at every launch
   int64_t group_chunk = n_groups / (static_cast<int64_t>(sms) * 8);

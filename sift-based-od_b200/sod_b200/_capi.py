@@ -89,6 +89,8 @@ _PROTOS = {
     "sod_hough_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "sod_hough_vote": (C.c_int, [C.POINTER(Scene), _p, _p, _i64, _p, _i32, _p, _i32, C.POINTER(HoughOut), _p,
                                  C.c_size_t, _p]),
+    "sod_hough_vote_dims": (C.c_int, [C.POINTER(Scene), _p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32,
+                                      C.POINTER(HoughOut), _p, C.c_size_t, _p]),
     "sod_affine_verify": (C.c_int, [C.POINTER(Scene), _p, _p, C.POINTER(HoughOut), _i32, _i32, _i32,
                                     C.c_double, C.c_double, _i32, C.POINTER(AffineOut), _p]),
 }

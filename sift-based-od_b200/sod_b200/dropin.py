@@ -73,9 +73,10 @@ def pose_bin_indices(poses, bins: int, width: int, height: int):
     return [decode_base_bin(b) for b in base[:n].cpu().numpy()]
 
 
-def hough_dict(matching_keypoints, width: int, height: int, bins: int, posebin_cls) -> dict:
+def hough_dict(matching_keypoints, width: int, height: int, bins, posebin_cls) -> dict:
     """Main.apply_hough_transform on the GPU: returns {(ix,iy,it,is): PoseBin} in the reference's
-    insertion order.  Each PoseBin also carries `_sod_members` (indices into matching_keypoints)."""
+    insertion order.  Each PoseBin also carries `_sod_members` (indices into matching_keypoints).
+    bins: one count, or (bin_x, bin_y, bin_theta, bin_sigma) for the legacy entry point."""
     n = len(matching_keypoints)
     if n == 0:
         return {}
@@ -86,7 +87,8 @@ def hough_dict(matching_keypoints, width: int, height: int, bins: int, posebin_c
     pose = res.pose[:n].cpu().numpy()
     out = {}
     code = h["code"].astype(np.int64)
-    keys = np.stack([code // bins ** 3, code // bins ** 2 % bins, code // bins % bins, code % bins], 1)
+    _, by, bt, bs = res.dims
+    keys = np.stack([code // (by * bt * bs), code // (bt * bs) % by, code // bs % bt, code % bs], 1)
     for i in range(h["n_bins"]):
         cnt = int(h["count"][i])
         off = int(h["offset"][i])

@@ -324,10 +324,11 @@ def compact_matches(idx: torch.Tensor, ok: torch.Tensor, t_lo: int = 0, t_hi: in
 class HoughResult:
     """Device outputs of sod_hough_vote plus the host view used to build PoseBin objects."""
 
-    def __init__(self, m_cap: int, n_groups: int, bins: int, device):
-        self.bins = bins
+    def __init__(self, m_cap: int, n_groups: int, bins, device):
+        self.dims = tuple(bins) if isinstance(bins, (tuple, list)) else (int(bins),) * 4
+        self.bins = self.dims[3]          # what sod_affine_verify decodes from a bin code: code % bins_sigma
         self.m_cap = m_cap
-        nb4 = bins ** 4
+        nb4 = int(np.prod(self.dims))
         self.cap_bins = max(1, min(16 * m_cap, n_groups * nb4))
         self.cap_votes = max(1, 16 * m_cap)
         e = lambda n, dt: torch.empty(n, dtype=dt, device=device)  # noqa: E731
@@ -366,12 +367,18 @@ class HoughResult:
 class HoughVoter:
     """Caches workspace / outputs across calls of the same capacity."""
 
-    def __init__(self, scene: SceneArrays, bins: int = 15):
-        if bins > _capi.MAX_BINS:
-            raise _capi.SodError(f"bins={bins} > {_capi.MAX_BINS}: not supported by the shared-memory histogram")
+    def __init__(self, scene: SceneArrays, bins=15):
+        """bins: one count for all four pose dimensions (main.py:89), or (bin_x, bin_y, bin_theta,
+        bin_sigma) as the legacy perform_hough_transform takes them (HoughTransform.py:8)."""
+        self.dims = tuple(int(b) for b in bins) if isinstance(bins, (tuple, list)) else (int(bins),) * 4
+        if len(self.dims) != 4 or min(self.dims) < 1:
+            raise ValueError("bins must be a positive int or four positive ints")
+        if max(self.dims) > 255 or int(np.prod(self.dims)) > _capi.MAX_BINS ** 4:
+            raise _capi.SodError(f"bins={bins}: more than {_capi.MAX_BINS}^4 counters are not supported by the "
+                                 f"shared-memory histogram")
         self.scene = scene
-        self.bins = int(bins)
-        self.lut = torch.tensor(sigma_lut(self.bins), dtype=torch.int32, device=scene.device)
+        self.bins = self.dims[0] if len(set(self.dims)) == 1 else None
+        self.lut = torch.tensor(sigma_lut(self.dims[3]), dtype=torch.int32, device=scene.device)
         self._ws = None
         self._res: HoughResult | None = None
 
@@ -387,13 +394,13 @@ class HoughVoter:
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=sc.device)
         if self._res is None or self._res.m_cap < m:
-            self._res = HoughResult(m, sc.n_groups, self.bins, sc.device)
+            self._res = HoughResult(m, sc.n_groups, self.dims, sc.device)
         res = self._res
         s, o = sc.struct(), res.struct()
-        check(lib.sod_hough_vote(C.byref(s), _ptr(match_q), _ptr(match_t), m, _ptr(n_dev), self.bins,
-                                 _ptr(self.lut), int(detail_min_count), C.byref(o), _ptr(self._ws),
-                                 self._ws.numel(), _stream()),
-              "sod_hough_vote")
+        check(lib.sod_hough_vote_dims(C.byref(s), _ptr(match_q), _ptr(match_t), m, _ptr(n_dev), *self.dims,
+                                      _ptr(self.lut), int(detail_min_count), C.byref(o), _ptr(self._ws),
+                                      self._ws.numel(), _stream()),
+              "sod_hough_vote_dims")
         return res
 
 

@@ -83,8 +83,15 @@ def test_helper_functions_match_oracle():
 
     table = perform_hough_transform(m.matching_keypoints, m.rgb_query)
     assert [list(k) for k in table.keys()] == z["bin_keys"].tolist()
-    with pytest.raises(NotImplementedError):
-        perform_hough_transform(m.matching_keypoints, m.rgb_query, bin_x=10)
+    # the legacy signature's separate bin counts (N4): same dict as the oracle's generalisation
+    scene = O.Scene(z["in_q_xy"], z["in_q_angle"], z["in_q_octave"], z["in_m_xy"], z["in_m_angle"],
+                    z["in_m_octave"], z["in_m_image"], z["in_img_centroid"], z["in_img_size"],
+                    int(z["in_width"]), int(z["in_height"]))
+    dims = (10, 12, 15, 6)
+    legacy = perform_hough_transform(m.matching_keypoints, m.rgb_query, *dims)
+    want_tab = O.hough_vote(scene, z["match_q"], z["match_t"], dims)
+    assert list(legacy.keys()) == [k[1:] for k in want_tab.keys()]
+    assert [b.votes for b in legacy.values()] == [b.votes for b in want_tab.values()]
 
     # single-bin helpers: one fit, then one residual pass
     big = max(table.values(), key=lambda b: b.votes)

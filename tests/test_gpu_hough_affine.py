@@ -160,3 +160,42 @@ def test_bins_above_limit_is_rejected_loudly():
     z = np.load(GOLD / "scene_tiny.npz")
     with pytest.raises(_capi.SodError):
         E.HoughVoter(_scene_arrays(z), 16)
+
+
+@pytest.mark.parametrize("dims", [(15, 12, 10, 6), (9, 15, 15, 15), (25, 25, 9, 9), (1, 1, 1, 1)])
+def test_per_dimension_bin_counts_vs_oracle(dims):
+    """sod_hough_vote_dims (legacy perform_hough_transform signature): keys in insertion order,
+    votes, members and means against the oracle's per-dimension restatement."""
+    from sod_b200 import engine as E
+    z = np.load(GOLD / "scene_multi.npz")
+    sc = _scene_arrays(z)
+    mq = torch.from_numpy(z["match_q"]).cuda()
+    mt = torch.from_numpy(z["match_t"]).cuda()
+    res = E.HoughVoter(sc, dims).vote(mq, mt)
+    h = res.host()
+    scene = O.Scene(z["in_q_xy"], z["in_q_angle"], z["in_q_octave"], z["in_m_xy"], z["in_m_angle"],
+                    z["in_m_octave"], z["in_m_image"], z["in_img_centroid"], z["in_img_size"],
+                    int(z["in_width"]), int(z["in_height"]))
+    table = O.hough_vote(scene, z["match_q"], z["match_t"], dims)
+    _, by, bt, bs = dims
+    code = h["code"].astype(np.int64)
+    keys = np.stack([code // (by * bt * bs), code // (bt * bs) % by, code // bs % bt, code % bs], 1)
+    assert [tuple(k) for k in keys.tolist()] == [k[1:] for k in table.keys()]
+    assert h["count"].tolist() == [b.votes for b in table.values()]
+    for i, b in enumerate(table.values()):
+        mem = h["members"][h["offset"][i]:h["offset"][i] + h["count"][i]]
+        assert mem.tolist() == b.members
+    want_mean = np.array([[b.centroid[0], b.centroid[1], b.angle, b.scale] for b in table.values()])
+    np.testing.assert_allclose(h["mean"][:, :4], want_mean, rtol=1e-12, atol=1e-9)
+    # the affine stage decodes the sigma index with the sigma count
+    aff = E.affine_verify(sc, mq, mt, res, 5, 4)
+    live = O.affine_verify(scene, z["match_q"], z["match_t"], O.valid_bins(table, 5), 4)
+    a = aff.host(h["n_votes"])
+    assert int(a["live"].sum()) == len(live)
+
+
+def test_too_many_counters_is_rejected_loudly():
+    from sod_b200 import _capi, engine as E
+    z = np.load(GOLD / "scene_tiny.npz")
+    with pytest.raises(_capi.SodError):
+        E.HoughVoter(_scene_arrays(z), (30, 30, 15, 15))
