@@ -108,3 +108,35 @@ def test_pack_from_f32_rejects_non_integer():
     x[3, 5] = 1.5
     with pytest.raises(ValueError):
         E.pack_descriptors(x)
+
+
+def _gpu_reference_top2(q, db):
+    """Exact top-2 on the GPU itself (fp64 matmul is exact for these magnitudes; ties -> lowest index
+    through an integer key), used where the numpy oracle would take minutes."""
+    qf, tf = q.double(), db.double()
+    d2 = (qf * qf).sum(1)[:, None] + (tf * tf).sum(1)[None, :] - 2.0 * (qf @ tf.T)
+    key = d2.round().long() * (1 << 32) + torch.arange(db.shape[0], device=q.device)[None, :]
+    best = torch.topk(key, min(2, db.shape[0]), dim=1, largest=False, sorted=True).values
+    idx = (best & 0xFFFFFFFF).int()
+    return idx, (best >> 32).int()
+
+
+def test_random_shapes_soak():
+    """Many random shapes, including the few-queries / large-database ones whose segments share their
+    thresholds through global memory, each run twice: results must be exact and repeatable."""
+    from sod_b200 import engine as E
+    rng = np.random.default_rng(2024)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    shapes = [(int(rng.integers(1, 3000)), int(rng.integers(2, 60000))) for _ in range(24)]
+    shapes += [(int(rng.integers(1, 600)), int(rng.integers(100000, 400000))) for _ in range(8)]
+    for nq, ndb in shapes:
+        hi = int(rng.choice([2, 16, 256]))       # small alphabets make ties frequent
+        q = torch.randint(0, hi, (nq, 128), dtype=torch.uint8, device="cuda", generator=g)
+        db = torch.randint(0, hi, (ndb, 128), dtype=torch.uint8, device="cuda", generator=g)
+        db[torch.randint(0, ndb, (min(nq, 50),), device="cuda", generator=g)] = q[:min(nq, 50)]
+        m = E.Matcher(E.prepare_db(db))
+        idx1, d1 = m.top2(q)
+        idx2, d2 = m.top2(q)
+        ridx, rd = _gpu_reference_top2(q, db)
+        assert torch.equal(idx1[:, :ridx.shape[1]], ridx) and torch.equal(d1[:, :rd.shape[1]], rd), (nq, ndb, hi)
+        assert torch.equal(idx1, idx2) and torch.equal(d1, d2), (nq, ndb, hi)
