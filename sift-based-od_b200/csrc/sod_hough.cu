@@ -212,19 +212,24 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
   }
 }
 
-__global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const int32_t* n_dev,
-                                     int64_t n_cap, int32_t* __restrict__ cursor,
-                                     int32_t* __restrict__ grouped) {
+// Counting-sort scatter: match id and its base bin travel together, so that the voting kernel reads
+// both with coalesced loads instead of gathering base_bin[grouped[p]] in each of its four phases.
+__global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const uint32_t* __restrict__ base_bin,
+                                     const int32_t* n_dev, int64_t n_cap, int32_t* __restrict__ cursor,
+                                     int32_t* __restrict__ grouped, uint32_t* __restrict__ grouped_base) {
   const int64_t n = live_count(n_dev, n_cap);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    grouped[atomicAdd(&cursor[group_of[i]], 1)] = static_cast<int32_t>(i);
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int pos = atomicAdd(&cursor[group_of[i]], 1);
+    grouped[pos] = static_cast<int32_t>(i);
+    grouped_base[pos] = base_bin[i];
+  }
 }
 
 struct VoteArgs {
   const int32_t* group_off;  // [n_groups+1]
   const int32_t* grouped;    // match ids grouped by Hough space
-  const uint32_t* base_bin;
+  const uint32_t* base_bin;  // base bins in the same (grouped) order
   uint16_t* creator;         // per grouped position: which of the 16 votes created its bin
   int64_t n_groups;
   Bins4 bins;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
     int my_bins = 0, my_votes = 0;
     for (int p = beg + tid; p < end; p += kVoteThreads) {
       unsigned created = 0;
-      for_each_vote(a.base_bin[a.grouped[p]], bins, [&](int o, int code) {
+      for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
         if (atomicAdd(&hist[code], 1u) == 0u) created |= 1u << o;
         ++my_votes;
       });
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
       for (int p = beg + tid; p < end; p += kVoteThreads) {
         const unsigned created = a.creator[p];
         if (!created) continue;
-        for_each_vote(a.base_bin[a.grouped[p]], bins, [&](int o, int code) {
+        for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
           if (!(created >> o & 1u)) return;
           const int cnt = static_cast<int>(hist[code]);
           const int rec = s_rec_base + atomicAdd(&s_rec_cur, 1);
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
     if (ok) {
       for (int p = beg + tid; p < end; p += kVoteThreads) {
         const int m = a.grouped[p];
-        for_each_vote(a.base_bin[m], bins,
+        for_each_vote(a.base_bin[p], bins,
                       [&](int, int code) { a.members_raw[atomicAdd(&hist[code], 1u)] = m; });
       }
     }
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
     for (int p = beg + tid; p < end; p += kVoteThreads) {
       const unsigned created = a.creator[p];
       if (!created) continue;
-      for_each_vote(a.base_bin[a.grouped[p]], bins, [&](int o, int code) {
+      for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
         if (created >> o & 1u) hist[code] = 0u;
       });
     }
@@ -536,6 +541,7 @@ size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
   int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket, *big_list;
+  uint32_t* grouped_base;
   int64_t big_cap;
   uint16_t* creator;
   size_t bytes;
@@ -555,6 +561,7 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.group_off = static_cast<int32_t*>(take((groups + 1) * 4));
   w.group_cursor = static_cast<int32_t*>(take((groups + 1) * 4));
   w.grouped = static_cast<int32_t*>(take(m * 4));
+  w.grouped_base = static_cast<uint32_t*>(take(m * 4));
   w.creator = static_cast<uint16_t*>(take(m * 2));
   w.members_raw = static_cast<int32_t*>(take(cap_votes * 4));
   w.big_cap = cap_votes / (kSmallBin + 1) + 1;
@@ -704,12 +711,12 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   SOD_CHECK_LAUNCH("hough_pose_kernel");
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.group_count, n_groups, w.group_off, w.group_cursor, nullptr);
   SOD_CHECK_LAUNCH("exclusive_scan_kernel");
-  group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(w.group_of, n_matches_dev,
-                                                                          n_matches, w.group_cursor, w.grouped);
+  group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+      w.group_of, out->base_bin, n_matches_dev, n_matches, w.group_cursor, w.grouped, w.grouped_base);
   SOD_CHECK_LAUNCH("group_scatter_kernel");
 
   VoteArgs va;
-  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = out->base_bin; va.creator = w.creator;
+  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.creator = w.creator;
   va.n_groups = n_groups; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
