@@ -7,14 +7,16 @@
 //
 // Kernel anatomy (one persistent CTA per SM, 640 threads):
 //   warp 0      TMA producer: query block (2 x 128 rows, double buffered) + database tiles
-//               (128 rows = 16 KB, kStages-deep ring) + the 528 B slice of per-row constants.
+//               (128 rows = 16 KB, kStages-deep ring) + the tile's 1040 B slice of per-row constants
+//               (|t|^2 << 8 | column, chunk minima, original rows) in its own, deeper ring.
 //   warps 1, 3  MMA issuers, one per query half: per database tile 4 UTCIMMA (M=128,N=128,K=32)
 //               each into four independent 128-column TMEM accumulator slots (2 halves x 2 buffers).
 //   warp 2      TMEM allocator.
 //   warps 4-19  epilogue: thread <-> query row (TMEM lane), 16 warps = 4 lane quadrants x 2 query
-//               halves x 2 column halves.  A warp pulls its 64 columns of the slot into registers,
-//               releases the slot at once, and prunes: a column can only enter the row's top-2 if
-//               |t|^2 - 2 q.t  <=  current 2nd best.  (Two threads per row: two candidate lists.)
+//               halves x 2 tile parities (even / odd tiles).  A warp pulls the 128 columns of its
+//               slot into registers in two loads, releases the slot, and prunes: a column can only
+//               enter the row's top-2 if |t|^2 - 2 q.t <= current 2nd best.  (Two threads per row:
+//               two candidate lists, merged by K3.)
 //
 // Pruning needs a bound that is tight PER ROW: a warp takes the slow path as soon as one of its 32
 // rows does.  sod_db_prepare therefore stores the database sorted by |t|^2, so that the smallest
