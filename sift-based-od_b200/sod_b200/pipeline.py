@@ -64,13 +64,21 @@ class DetectionPipeline:
         _, _, self.row_lo, self.row_hi = shard_bounds(n_images, rows, rank, world)
         des = db.des[self.row_lo:self.row_hi]
         des_dev = (des if isinstance(des, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(des)))
-        self.shard = E.prepare_db(des_dev.to(self.device).contiguous(), index_base=self.row_lo)
-        self.matcher = E.Matcher(self.shard)
+        des_dev = des_dev.to(self.device).contiguous()
+        # u8 descriptors (what OpenCV SIFT produces) take the exact kind::i8 matcher; float32 descriptors
+        # the bf16 path with its stated tolerance (include/sod.h) - queries must then be float32 too.
+        self.float_path = des_dev.dtype == torch.float32
+        if self.float_path:
+            self.shard = E.prepare_db_float(des_dev, index_base=self.row_lo)
+            self.matcher = E.FloatMatcher(self.shard)
+        else:
+            self.shard = E.prepare_db(des_dev, index_base=self.row_lo)
+            self.matcher = E.Matcher(self.shard)
         self.max_queries = int(max_queries)
         nq = self.max_queries
         dev = self.device
         # query-side device buffers (filled by copy for host inputs, pointers stay stable)
-        self.q_des = torch.empty((nq, 128), dtype=torch.uint8, device=dev)
+        self.q_des = torch.empty((nq, 128), dtype=torch.float32 if self.float_path else torch.uint8, device=dev)
         self.scene = E.SceneArrays(
             torch.zeros((nq, 2), dtype=torch.float32), torch.zeros(nq, dtype=torch.float32),
             torch.zeros(nq, dtype=torch.int32), db.xy, db.angle, db.octave, db.image, db.img_centroid,
@@ -87,7 +95,8 @@ class DetectionPipeline:
         self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
         if world > 1:
             self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
-            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32 if self.float_path else torch.int32,
+                                          device=dev)
         self.launches_per_call = 16  # our kernels per detect_device call
 
     # ---------------------------------------------------------------- device-resident inputs
@@ -131,6 +140,7 @@ class DetectionPipeline:
         self.q_des, sc.q_xy, sc.q_angle, sc.q_octave, sc.q_frame = (qs["des"], qs["xy"], qs["angle"], qs["octave"],
                                                                     qs["frame"])
         q = self.q_des[:n]
+        merge = E.merge_top2_float if self.float_path else E.merge_top2
         idx, d2 = self.matcher.top2(q)
         if self.world > 1:
             import torch.distributed as dist
@@ -140,12 +150,12 @@ class DetectionPipeline:
                 dist.all_gather_into_tensor(gd, d2, group=self.group)
             else:
                 gi = torch.empty((self.world, n, 2), dtype=torch.int32, device=self.device)
-                gd = torch.empty_like(gi)
+                gd = torch.empty((self.world, n, 2), dtype=d2.dtype, device=self.device)
                 dist.all_gather_into_tensor(gi, idx, group=self.group)
                 dist.all_gather_into_tensor(gd, d2, group=self.group)
-            idx, d2, dist_f, ok = E.merge_top2(gi, gd)
+            idx, d2, dist_f, ok = merge(gi, gd)
         else:
-            idx, d2, dist_f, ok = E.merge_top2(idx[None], d2[None])
+            idx, d2, dist_f, ok = merge(idx[None], d2[None])
         lo, hi = (self.row_lo, self.row_hi) if self.world > 1 else (0, 2 ** 31 - 1)
         mq, mt, n_dev = E.compact_matches(idx, ok, lo, hi)
         hough = self.voter.vote(mq, mt, n_dev, detail_min_count=self.vote_threshold)

@@ -61,3 +61,24 @@ def test_overlapped_batches_equal_one_at_a_time():
         for k in ("valid_group", "valid_code", "votes", "status", "params"):
             np.testing.assert_array_equal(g[k][og], w[k][ow])
     assert not np.array_equal(want[0]["idx"], want[1]["idx"])
+
+
+def test_float_descriptors_take_the_bf16_path_through_the_pipeline():
+    """Halved (non-integer) descriptors as float32: every product stays exact in the hi/lo split, so
+    the whole pipeline must end at the reference's final pose."""
+    from sod_b200.pipeline import DetectionPipeline, ModelDatabase
+    z = np.load(GOLD / "scene_multi.npz")
+    db = ModelDatabase(z["in_m_des"].astype(np.float32) * np.float32(0.5), z["in_m_xy"], z["in_m_angle"],
+                       z["in_m_octave"], z["in_m_image"], z["in_img_centroid"], z["in_img_size"])
+    nq = len(z["in_q_xy"])
+    pipe = DetectionPipeline(db, nq, np.array([[int(z["in_width"]), int(z["in_height"])]], np.int32),
+                             per_object_spaces=False)
+    assert pipe.float_path
+    out = pipe.detect(z["in_q_des"].astype(np.float32) * np.float32(0.5), z["in_q_xy"], z["in_q_angle"],
+                      z["in_q_octave"], np.zeros(nq, np.int32))
+    assert out["n_matches"] == len(z["match_q"])
+    np.testing.assert_array_equal(np.nonzero(out["ok"])[0], z["match_q"])
+    np.testing.assert_array_equal(out["idx"][out["ok"].astype(bool), 0], z["match_t"])
+    poses = pipe.final_poses(out)
+    got = np.array([[c[0], c[1], o, s, sh[0], sh[1]] for (c, o, s, sh) in poses.get(0, [])], np.float64).reshape(-1, 6)
+    np.testing.assert_allclose(got, z["final_pose"], rtol=1e-10, atol=1e-9)
