@@ -53,7 +53,7 @@ def test_stream_equals_main_flow_and_finds_the_objects():
         for (o, s, deg, cx, cy) in pl:
             fr, m = imaging.place(rng, fr, objs[o], s, deg, cx, cy)
             c = db.img_centroid[o]
-            t.append((m @ np.array([c[0], c[1], 1.0]), s))
+            t.append((m @ np.array([c[0], c[1], 1.0]), s, deg))
         frames.append(fr)
         truth.append(t)
 
@@ -79,10 +79,12 @@ def test_stream_equals_main_flow_and_finds_the_objects():
         assert got.shape == want.shape
         np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
         # and every planted object has a final pose at its centroid with its scale
-        for (xy, s) in truth[i]:
+        for (xy, s, deg) in truth[i]:     # position, scale octave and orientation are recovered
             d = np.hypot(got[:, 0] - xy[0], got[:, 1] - xy[1]) if len(got) else np.array([np.inf])
             j = int(d.argmin())
             assert d[j] < 40, (i, xy, got[:, :2])
             assert 0.5 * s <= got[j, 3] <= 2.0 * s
+            err = (np.degrees(got[j, 2]) - deg + 180.0) % 360.0 - 180.0
+            assert abs(err) < 3.0, (i, deg, np.degrees(got[j, 2]))
         if not truth[i]:
             assert len(got) == 0
