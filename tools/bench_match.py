@@ -24,6 +24,12 @@ def run(nq, ndb, iters=10, kind="uniform"):
     if kind == "uniform":
         q = torch.randint(0, 256, (nq, 128), dtype=torch.uint8, device="cuda", generator=g)
         db = torch.randint(0, 256, (ndb, 128), dtype=torch.uint8, device="cuda", generator=g)
+    elif kind == "noevent":
+        # all-zero queries + two all-zero database rows (smallest norm -> first tile): the threshold is 0
+        # after the first tile and nothing passes the bound any more: the shipped binary without updates
+        q = torch.zeros((nq, 128), dtype=torch.uint8, device="cuda")
+        db = sift_like_gpu(ndb, g)
+        db[:2] = 0
     else:
         q, db = sift_like_gpu(nq, g), sift_like_gpu(ndb, g)
     m = E.Matcher(E.prepare_db(db))
