@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import pickle
 from dataclasses import dataclass, fields
-from pathlib import Path
 
 import numpy as np
 

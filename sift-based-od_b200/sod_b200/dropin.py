@@ -11,7 +11,6 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _capi
 from . import engine as E
 from ._capi import check, lib
 

@@ -1,6 +1,5 @@
 """CPU-side checks of the boundary: the library builds, loads without a GPU, exports exactly the
 functions include/sod.h declares, and argument errors are reported through status codes."""
-import ctypes as C
 import re
 import subprocess
 from pathlib import Path
