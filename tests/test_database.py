@@ -75,3 +75,30 @@ def test_empty_database():
     db = PackedDatabase.from_reference_rows([])
     db.validate()
     assert len(db) == 0 and db.n_images == 0 and db.to_reference_rows() == []
+
+
+def test_build_database_writes_both_formats(tmp_path):
+    """GenerateDatabaseInfo.build_database (drop-in for GenerateDatabaseInfo.py:14-37) on images on
+    disk: reference row layout in the pickle, the same content in the packed file."""
+    import cv2
+    import GenerateDatabaseInfo as G
+    import imaging
+    rng = np.random.default_rng(4)
+    img_dir = tmp_path / "train"
+    img_dir.mkdir()
+    for i, (w, h) in enumerate([(300, 200), (240, 320)]):
+        cv2.imwrite(str(img_dir / f"obj{i}.png"), imaging.textured(rng, w, h, shapes=40))
+    (img_dir / "notes.txt").write_text("not an image")          # skipped, as cv2.imread returns None
+    rows = G.build_database(str(img_dir), str(tmp_path / "training_data.pkl"), str(tmp_path / "training_data.sodb"))
+    assert len(rows) == 2
+    for temp_kp, des, img_size, centroid, path in rows:
+        assert img_size[0] == 1500 and des.shape == (len(temp_kp), 128) and len(temp_kp) > 50   # :23-24 resize
+        assert des.dtype == np.float32 and np.array_equal(des, np.rint(des)) and des.max() <= 255  # SURVEY T1
+        xs = [t[0][0] for t in temp_kp]
+        assert abs(centroid[0] - sum(xs) / len(xs)) < 1e-9 and str(path).endswith(".png")
+    with open(tmp_path / "training_data.pkl", "rb") as f:
+        _same_rows(pickle.load(f), rows)
+    a = PackedDatabase.open(tmp_path / "training_data.pkl")
+    b = PackedDatabase.open(tmp_path / "training_data.sodb")
+    assert np.array_equal(a.des, b.des) and np.array_equal(a.xy, b.xy) and np.array_equal(a.img_size, b.img_size)
+    assert a.n_images == 2 and len(a) == sum(len(r[0]) for r in rows)
