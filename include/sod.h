@@ -82,6 +82,20 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
                    const int32_t* cq, int64_t n_db, int32_t db_index_base, int32_t* out_idx,
                    uint32_t* out_d2, void* workspace, size_t workspace_bytes, sod_stream_t stream);
 
+/* sod_match_top2 over the stored tiles [tile_begin, tile_end) only (tile_end < 0: to the end; a tile is
+ * SOD_TILE_ROWS stored rows, in the order sod_db_prepare wrote them: an even sample of the norm range),
+ * with an optional caller-held threshold array row_thr: int32 [sod_row_thr_ints(n_query)], in units of
+ * d^2 - |q|^2, 0x7F7F7F7F = none.  The sweep prunes with it from the start and leaves
+ * min(input, the row's 2nd best of this sweep) in it.  Any such value is an upper bound of the row's final
+ * 2nd best, so results stay exact when the array is carried to another launch, or min-reduced across the
+ * GPUs that hold other shards before each sweeps the rest of its shard: candidates that cannot be in the
+ * GLOBAL top-2 are then never collected.  Lists of several ranges are combined with sod_top2_merge. */
+int64_t sod_row_thr_ints(int64_t n_query);
+int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
+                         const int32_t* cq, int64_t n_db, int32_t db_index_base, int64_t tile_begin,
+                         int64_t tile_end, int32_t* row_thr, int32_t* out_idx, uint32_t* out_d2,
+                         void* workspace, size_t workspace_bytes, sod_stream_t stream);
+
 /* K3.  Merge n_parts candidate lists (parts_idx/parts_d2 are [n_parts][n_query][2], e.g. the
  * all-gathered shard-local results) into the global top-2 by (d2, idx) lexicographic order and
  * apply Lowe's ratio test exactly as the reference evaluates it (main.py:81-82):

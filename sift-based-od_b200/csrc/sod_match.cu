@@ -80,7 +80,8 @@ struct MatchArgs {
   int32_t* part_idx;   // [n_seg * 2][nq][2]
   int32_t* row_thr;    // [n_qblocks * 256] shared pruning thresholds (memset to 0x7F..), or nullptr
   int nq;
-  int n_tiles;
+  int n_tiles;         // tiles swept by this launch: [tile_begin, tile_begin + n_tiles)
+  int tile_begin;
   int n_qblocks;
   int n_seg;
   int idx_base;
@@ -227,8 +228,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
         const int seg = u / a.n_qblocks;
         const int qb = u - seg * a.n_qblocks;
-        const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
-        const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
+        const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
+        const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
         const uint32_t ab = ucount & 1u, aph = (ucount >> 1) & 1u;
         mbar_wait(bar_aempty(ab), aph ^ 1u);
         mbar_arrive_expect_tx(bar_afull(ab), kHalves * kTileBytes);
@@ -265,8 +266,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint32_t step = 0, ucount = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
       const int seg = u / a.n_qblocks;
-      const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
-      const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
+      const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
+      const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const uint32_t ab = ucount & 1u, aph = (ucount >> 1) & 1u;
       mbar_wait(bar_afull(ab), aph);
       const uint64_t adesc = umma_desc_k128(base + kOffA + (ab * kHalves + h) * kTileBytes);
@@ -304,8 +305,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
       const int seg = u / a.n_qblocks;
       const int qb = u - seg * a.n_qblocks;
-      const int t0 = static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
-      const int t1 = static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
+      const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
+      const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
       Top2 best{kNoKey64, kNoKey64, kNoKey};
       // Threshold sharing between the units that sweep different database segments for the same
@@ -660,6 +661,10 @@ static size_t match_workspace_need(const Plan& p, int64_t n_query) {
   return match_lists_bytes(p, n_query) + static_cast<size_t>(p.n_qblocks) * kBlockQ * 4;
 }
 
+int64_t sod_row_thr_ints(int64_t n_query) {
+  return n_query <= 0 ? 0 : (n_query + kBlockQ - 1) / kBlockQ * kBlockQ;
+}
+
 size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db) {
   if (n_query <= 0 || n_db <= 0) return 16;
   const int sms = device_sm_count();
@@ -670,6 +675,14 @@ size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db) {
 int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
                    const int32_t* cq, int64_t n_db, int32_t db_index_base, int32_t* out_idx,
                    uint32_t* out_d2, void* workspace, size_t workspace_bytes, sod_stream_t stream) {
+  return sod_match_top2_range(q, qn, n_query, db_sorted, cq, n_db, db_index_base, 0, -1, nullptr, out_idx, out_d2,
+                              workspace, workspace_bytes, stream);
+}
+
+int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
+                         const int32_t* cq, int64_t n_db, int32_t db_index_base, int64_t tile_begin,
+                         int64_t tile_end, int32_t* row_thr, int32_t* out_idx, uint32_t* out_d2,
+                         void* workspace, size_t workspace_bytes, sod_stream_t stream) {
   SOD_CHECK_ARG(n_query >= 0 && n_db >= 0, "negative size");
   SOD_CHECK_ARG(n_query < (int64_t(1) << 31) - kBlockQ && n_db < (int64_t(1) << 31) - kTileN,
                 "size out of range");
@@ -680,7 +693,10 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mthreads = 128;
   const unsigned mblocks = static_cast<unsigned>((n_query + mthreads - 1) / mthreads);
-  if (n_db == 0) {
+  const int64_t all_tiles = (n_db + kTileN - 1) / kTileN;
+  if (tile_end < 0) tile_end = all_tiles;
+  SOD_CHECK_ARG(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= all_tiles, "tile range out of bounds");
+  if (n_db == 0 || tile_begin == tile_end) {
     top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(nullptr, nullptr, 0, n_query, out_idx, out_d2,
                                                     nullptr, nullptr, 0.0);
     SOD_CHECK_LAUNCH("top2_merge_kernel");
@@ -694,7 +710,7 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
                 "q, db, cq and workspace must be 16-byte aligned");
   const int sms = device_sm_count();
   if (sms <= 0) return SOD_ERR_CUDA;
-  const Plan p = make_plan(n_query, n_db, sms);
+  const Plan p = make_plan(n_query, (tile_end - tile_begin) * kTileN, sms);
   const size_t need = match_workspace_need(p, n_query);
   SOD_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
 
@@ -710,13 +726,16 @@ int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const u
   a.part_d2 = static_cast<uint32_t*>(workspace);
   a.part_idx = reinterpret_cast<int32_t*>(a.part_d2 + static_cast<size_t>(p.n_seg) * kParity * n_query * 2);
   // Thresholds are shared whenever a query row is swept by more than one unit; 0x7F7F7F7F = none yet
-  a.row_thr = nullptr;
-  if (p.n_seg > 1) {
+  // A caller-held array additionally carries thresholds across launches (and, after a min-reduce, across
+  // the shards of several GPUs): it is read at the start and holds min(input, this sweep's 2nd best) after.
+  a.row_thr = row_thr;
+  if (!row_thr && p.n_seg > 1) {
     a.row_thr = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + match_lists_bytes(p, n_query));
     SOD_CHECK_CUDA(cudaMemsetAsync(a.row_thr, 0x7F, static_cast<size_t>(p.n_qblocks) * kBlockQ * 4, st));
   }
   a.nq = static_cast<int>(n_query);
   a.n_tiles = p.n_tiles;
+  a.tile_begin = static_cast<int>(tile_begin);
   a.n_qblocks = p.n_qblocks;
   a.n_seg = p.n_seg;
   a.idx_base = db_index_base;

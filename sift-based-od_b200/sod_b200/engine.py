@@ -95,8 +95,17 @@ class Matcher:
         self._qn: torch.Tensor | None = None
         self.events: list | None = None   # if a list: (start, end) CUDA events around sod_match_top2
 
-    def _scratch(self, nq: int) -> tuple[torch.Tensor, torch.Tensor]:
-        need = int(lib.sod_match_workspace_bytes(nq, self.shard.n))
+    @property
+    def n_tiles(self) -> int:
+        return (self.shard.n + _capi.TILE_ROWS - 1) // _capi.TILE_ROWS
+
+    def new_thresholds(self, nq: int) -> torch.Tensor:
+        """A caller-held threshold array for top2(..., row_thr=...): all "none yet"."""
+        return torch.full((max(int(lib.sod_row_thr_ints(nq)), 1),), 0x7F7F7F7F, dtype=torch.int32,
+                          device=self.shard.des.device)
+
+    def _scratch(self, nq: int, rows: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        need = int(lib.sod_match_workspace_bytes(nq, self.shard.n if rows is None else rows))
         dev = self.shard.des.device
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -104,21 +113,27 @@ class Matcher:
             self._qn = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
         return self._ws, self._qn
 
-    def top2(self, q_u8: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        """-> (idx int32 [nq,2] global rows or -1, d2 int32 [nq,2] squared distances, -1 if none)."""
+    def top2(self, q_u8: torch.Tensor, tiles: tuple[int, int] | None = None, row_thr: torch.Tensor | None = None,
+             prepared: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+        """-> (idx int32 [nq,2] global rows or -1, d2 int32 [nq,2] squared distances, -1 if none).
+        tiles=(begin, end): sweep only these stored 128-row tiles; row_thr: threshold array from
+        new_thresholds(), read at the start and updated (sod_match_top2_range); prepared=True reuses the
+        query norms of the previous call with the same queries."""
         q_u8 = _require_cuda(q_u8, torch.uint8, "query descriptors")
         nq = int(q_u8.shape[0])
-        ws, qn = self._scratch(nq)
+        t0, t1 = (0, self.n_tiles) if tiles is None else (int(tiles[0]), int(tiles[1]))
+        ws, qn = self._scratch(nq, (t1 - t0) * _capi.TILE_ROWS)
         idx = torch.empty((nq, 2), dtype=torch.int32, device=q_u8.device)
         d2 = torch.empty((nq, 2), dtype=torch.int32, device=q_u8.device)
         s = self.shard
-        check(lib.sod_query_prepare(_ptr(q_u8), nq, _ptr(qn), _stream()), "sod_query_prepare")
+        if not prepared:
+            check(lib.sod_query_prepare(_ptr(q_u8), nq, _ptr(qn), _stream()), "sod_query_prepare")
         if self.events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.sod_match_top2(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n,
-                                 s.index_base, _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(), _stream()),
-              "sod_match_top2")
+        check(lib.sod_match_top2_range(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n, s.index_base, t0, t1,
+                                       _ptr(row_thr), _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(), _stream()),
+              "sod_match_top2_range")
         if self.events is not None:
             e1.record()
             self.events.append((e0, e1))

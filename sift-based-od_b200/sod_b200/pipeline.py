@@ -68,12 +68,18 @@ class DetectionPipeline:
         # u8 descriptors (what OpenCV SIFT produces) take the exact kind::i8 matcher; float32 descriptors
         # the bf16 path with its stated tolerance (include/sod.h) - queries must then be float32 too.
         self.float_path = des_dev.dtype == torch.float32
+        self.seed_tiles = 0
         if self.float_path:
             self.shard = E.prepare_db_float(des_dev, index_base=self.row_lo)
             self.matcher = E.FloatMatcher(self.shard)
         else:
             self.shard = E.prepare_db(des_dev, index_base=self.row_lo)
             self.matcher = E.Matcher(self.shard)
+            # database-sharded runs sweep this many stored tiles before the ranks exchange thresholds
+            # (the decision must be the same on every rank: it depends on the whole database only)
+            n_tiles = self.matcher.n_tiles
+            if world > 1 and len(image) // world >= 64 * 128:
+                self.seed_tiles = min(max(16, n_tiles // 8), n_tiles)
         self.max_queries = int(max_queries)
         nq = self.max_queries
         dev = self.device
@@ -97,7 +103,9 @@ class DetectionPipeline:
             self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
             self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32 if self.float_path else torch.int32,
                                           device=dev)
-        self.launches_per_call = 16  # our kernels per detect_device call
+        # our kernels per detect_device call; the sample sweep of a database-sharded run adds
+        # one match launch and two list merges
+        self.launches_per_call = 16 + (3 if self.seed_tiles else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
     def _qset(self, slot: int) -> dict:
@@ -141,7 +149,21 @@ class DetectionPipeline:
                                                                     qs["frame"])
         q = self.q_des[:n]
         merge = E.merge_top2_float if self.float_path else E.merge_top2
-        idx, d2 = self.matcher.top2(q)
+        if self.world > 1 and not self.float_path and self.seed_tiles > 0:
+            # Two sweeps per shard with one exchange in between: every rank first sweeps a sample of its
+            # shard (the first stored tiles: an even sample of the norm range), the ranks min-reduce the
+            # rows' 2nd-best bounds (4 B per query row), and the rest of each shard is swept with the
+            # GLOBAL bound from its first tile on.  Without this every shard re-establishes its own
+            # thresholds, which costs ~2 ln(n) slow-path updates per row and shard.
+            import torch.distributed as dist
+            m = self.matcher
+            thr = m.new_thresholds(n)
+            i1, d1 = m.top2(q, (0, self.seed_tiles), thr)
+            dist.all_reduce(thr, op=dist.ReduceOp.MIN, group=self.group)
+            i2, d2b = m.top2(q, (self.seed_tiles, m.n_tiles), thr, prepared=True)
+            idx, d2 = E.merge_top2(torch.stack([i1, i2]), torch.stack([d1, d2b]))[:2]
+        else:
+            idx, d2 = self.matcher.top2(q)
         if self.world > 1:
             import torch.distributed as dist
             gi, gd = self._gather_idx[:, :n], self._gather_d2[:, :n]

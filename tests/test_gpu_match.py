@@ -140,3 +140,35 @@ def test_random_shapes_soak():
         ridx, rd = _gpu_reference_top2(q, db)
         assert torch.equal(idx1[:, :ridx.shape[1]], ridx) and torch.equal(d1[:, :rd.shape[1]], rd), (nq, ndb, hi)
         assert torch.equal(idx1, idx2) and torch.equal(d1, d2), (nq, ndb, hi)
+
+
+def test_tile_ranges_and_carried_thresholds_stay_exact():
+    """sod_match_top2_range: (a) lists of disjoint tile ranges merge to the full result, with and
+    without a carried threshold array; (b) a threshold array preset to the exact final 2nd best (the
+    tightest bound another shard could ever supply) still yields the exact top-2, ties included."""
+    from sod_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for nq, ndb, hi in ((700, 30000, 256), (3000, 9000, 4), (130, 70000, 256)):
+        q = torch.randint(0, hi, (nq, 128), dtype=torch.uint8, device="cuda", generator=g)
+        db = torch.randint(0, hi, (ndb, 128), dtype=torch.uint8, device="cuda", generator=g)
+        db[torch.randint(0, ndb, (64,), device="cuda", generator=g)] = q[:64]
+        m = E.Matcher(E.prepare_db(db, index_base=5))
+        full_i, full_d = m.top2(q)
+        nt = m.n_tiles
+        cut = max(1, nt // 8)
+        for carry in (False, True):
+            thr = m.new_thresholds(nq) if carry else None
+            i1, d1 = m.top2(q, (0, cut), thr)
+            i2, d2 = m.top2(q, (cut, nt), thr, prepared=True)
+            mi, md = E.merge_top2(torch.stack([i1, i2]), torch.stack([d1, d2]))[:2]
+            assert torch.equal(mi, full_i) and torch.equal(md, full_d), (nq, ndb, carry)
+        # thresholds as tight as they can ever get: d2 of the true 2nd best minus |q|^2
+        qn = (q.int() ** 2).sum(1)
+        thr = m.new_thresholds(nq)
+        thr[:nq] = full_d[:, 1] - qn
+        ti, td = m.top2(q, None, thr)
+        assert torch.equal(ti, full_i) and torch.equal(td, full_d), (nq, ndb, "preset")
+        # an empty range returns empty lists and leaves the thresholds alone
+        before = thr.clone()
+        ei, ed = m.top2(q, (3, 3), thr)
+        assert (ei == -1).all() and torch.equal(thr, before)
