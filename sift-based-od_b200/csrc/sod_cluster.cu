@@ -10,13 +10,14 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Loads go to L2 (__ldcg): another SM's hook must not hide behind a stale L1 line.
 __device__ __forceinline__ int uf_find(int* parent, int x) {
-  int p = parent[x];
+  int p = __ldcg(parent + x);
   while (p != x) {  // path halving; parents only ever decrease, so stale reads are still ancestors
-    const int g = parent[p];
+    const int g = __ldcg(parent + p);
     if (g != p) parent[x] = g;
     x = p;
-    p = parent[x];
+    p = __ldcg(parent + x);
   }
   return x;
 }
@@ -41,9 +42,18 @@ __global__ void label_init_kernel(int* __restrict__ label, int n) {
   if (i < n) label[i] = i;
 }
 
+// Final labels.  No path compression here: a halving store that was computed from older parents could
+// land after a thread has written its final label and replace it by a mere ancestor.  The walk only
+// reads; the one store per thread writes a root, which is a valid parent for every concurrent reader.
 __global__ void label_flatten_kernel(int* __restrict__ label, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) label[i] = uf_find(label, i);
+  if (i >= n) return;
+  int x = i, p = __ldcg(label + x);
+  while (p != x) {
+    x = p;
+    p = __ldcg(label + x);
+  }
+  label[i] = x;
 }
 
 // One CTA per bin i; its warps sweep the other bins 32 at a time (lane <-> j), __ballot_sync builds the
