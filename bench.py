@@ -329,6 +329,8 @@ def run_ours(args):
         r = pipe.detect_device(nq)
     barrier()
     pipe.matcher.events = []
+    if pipe.seed_matcher is not None:   # the threshold-seeding sweep of a database-sharded run counts too
+        pipe.seed_matcher.events = pipe.matcher.events
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -339,8 +341,10 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     match_events, pipe.matcher.events = pipe.matcher.events, None
+    if pipe.seed_matcher is not None:
+        pipe.seed_matcher.events = None
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    # (a database-sharded step has two match launches: the sample sweep and the rest of the shard)
+    # (a database-sharded step has two match launches: the seeding sweep and the shard sweep)
     match_ms = torch.tensor([float(np.sum([a.elapsed_time(b) for a, b in match_events])) / args.steps], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -501,6 +501,26 @@ __global__ void pack_u8_kernel(const float4* __restrict__ src, int64_t n_vec4,
   if (bad) atomicOr(nonint_flag, 1);
 }
 
+// Output of one merged row + the ratio test exactly as the reference evaluates it (main.py:81-82).
+__device__ __forceinline__ void write_top2_row(int64_t row, int32_t i1, uint32_t d1, int32_t i2, uint32_t d2,
+                                               int32_t* __restrict__ out_idx, uint32_t* __restrict__ out_d2,
+                                               float* __restrict__ out_dist, uint8_t* __restrict__ out_pass,
+                                               double ratio) {
+  out_idx[row * 2 + 0] = i1;
+  out_idx[row * 2 + 1] = i2;
+  out_d2[row * 2 + 0] = d1;
+  out_d2[row * 2 + 1] = d2;
+  // OpenCV reports sqrt of the float32 squared distance; d2 < 2^24 converts exactly.
+  const float f1 = (i1 >= 0) ? __fsqrt_rn(static_cast<float>(d1)) : __int_as_float(0x7f800000);
+  const float f2 = (i2 >= 0) ? __fsqrt_rn(static_cast<float>(d2)) : __int_as_float(0x7f800000);
+  if (out_dist) {
+    out_dist[row * 2 + 0] = f1;
+    out_dist[row * 2 + 1] = f2;
+  }
+  if (out_pass)
+    out_pass[row] = (i2 >= 0 && static_cast<double>(f1) < ratio * static_cast<double>(f2)) ? 1 : 0;
+}
+
 // K3: merge candidate lists, exact ratio test.
 __global__ void top2_merge_kernel(const int32_t* __restrict__ parts_idx,
                                   const uint32_t* __restrict__ parts_d2, int n_parts, int64_t nq,
@@ -530,19 +550,48 @@ __global__ void top2_merge_kernel(const int32_t* __restrict__ parts_idx,
       }
     }
   }
-  out_idx[row * 2 + 0] = i1;
-  out_idx[row * 2 + 1] = i2;
-  out_d2[row * 2 + 0] = d1;
-  out_d2[row * 2 + 1] = d2;
-  // OpenCV reports sqrt of the float32 squared distance; d2 < 2^24 converts exactly.
-  const float f1 = (i1 >= 0) ? __fsqrt_rn(static_cast<float>(d1)) : __int_as_float(0x7f800000);
-  const float f2 = (i2 >= 0) ? __fsqrt_rn(static_cast<float>(d2)) : __int_as_float(0x7f800000);
-  if (out_dist) {
-    out_dist[row * 2 + 0] = f1;
-    out_dist[row * 2 + 1] = f2;
-  }
-  if (out_pass)
-    out_pass[row] = (i2 >= 0 && static_cast<double>(f1) < ratio * static_cast<double>(f2)) ? 1 : 0;
+  write_top2_row(row, i1, d1, i2, d2, out_idx, out_d2, out_dist, out_pass, ratio);
+}
+
+// K3, collective form.  A candidate as one signed 64-bit key (d2 << 32 | global row): signed order is
+// the (distance, index) order of the merge, so the MIN of the ranks' keys IS the merged best - an
+// all-reduce (in-switch on NVSwitch) replaces gathering every rank's lists.  No entry: kNoneKey.
+constexpr long long kNoneKey = 0x7FFFFFFFFFFFFFFFll;
+
+__global__ void top2_keys_kernel(const int32_t* __restrict__ idx, const uint32_t* __restrict__ d2, int64_t nq,
+                                 long long* __restrict__ own, long long* __restrict__ best) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  const int2 ci = *reinterpret_cast<const int2*>(idx + row * 2);
+  const uint2 cd = *reinterpret_cast<const uint2*>(d2 + row * 2);
+  const long long k1 = ci.x < 0 ? kNoneKey : (static_cast<long long>(cd.x) << 32) | static_cast<uint32_t>(ci.x);
+  const long long k2 = ci.y < 0 ? kNoneKey : (static_cast<long long>(cd.y) << 32) | static_cast<uint32_t>(ci.y);
+  own[row] = k1;
+  own[nq + row] = k2;
+  best[row] = k1;
+}
+
+// After best = MIN over ranks: the rank that owns the global best offers its own 2nd, every other rank
+// its 1st; the MIN of these is the global 2nd (database rows live on exactly one rank).
+__global__ void top2_runner_up_kernel(const long long* __restrict__ best, const long long* __restrict__ own,
+                                      int64_t nq, long long* __restrict__ runner_up) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  const long long k1 = own[row];
+  runner_up[row] = k1 == best[row] ? own[nq + row] : k1;
+}
+
+__global__ void top2_from_keys_kernel(const long long* __restrict__ best, const long long* __restrict__ second,
+                                      int64_t nq, int32_t* __restrict__ out_idx, uint32_t* __restrict__ out_d2,
+                                      float* __restrict__ out_dist, uint8_t* __restrict__ out_pass, double ratio) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  const long long k1 = best[row], k2 = second[row];
+  const bool h1 = k1 != kNoneKey, h2 = k2 != kNoneKey;
+  write_top2_row(row, h1 ? static_cast<int32_t>(k1 & 0xFFFFFFFFll) : -1,
+                 h1 ? static_cast<uint32_t>(k1 >> 32) : 0xFFFFFFFFu,
+                 h2 ? static_cast<int32_t>(k2 & 0xFFFFFFFFll) : -1,
+                 h2 ? static_cast<uint32_t>(k2 >> 32) : 0xFFFFFFFFu, out_idx, out_d2, out_dist, out_pass, ratio);
 }
 
 struct Plan {
@@ -763,6 +812,47 @@ int sod_top2_merge(const int32_t* parts_idx, const uint32_t* parts_d2, int32_t n
                       static_cast<cudaStream_t>(stream)>>>(parts_idx, parts_d2, n_parts, n_query,
                                                            out_idx, out_d2, out_dist, out_pass, ratio);
   SOD_CHECK_LAUNCH("top2_merge_kernel");
+  return SOD_OK;
+}
+
+int sod_top2_keys(const int32_t* idx, const uint32_t* d2, int64_t n_query, int64_t* own, int64_t* best,
+                  sod_stream_t stream) {
+  SOD_CHECK_ARG(n_query >= 0, "negative size");
+  if (n_query == 0) return SOD_OK;
+  SOD_CHECK_ARG(idx && d2 && own && best, "null pointer");
+  const int threads = 256;
+  top2_keys_kernel<<<static_cast<unsigned>((n_query + threads - 1) / threads), threads, 0,
+                     static_cast<cudaStream_t>(stream)>>>(idx, d2, n_query, reinterpret_cast<long long*>(own),
+                                                          reinterpret_cast<long long*>(best));
+  SOD_CHECK_LAUNCH("top2_keys_kernel");
+  return SOD_OK;
+}
+
+int sod_top2_runner_up(const int64_t* best, const int64_t* own, int64_t n_query, int64_t* runner_up,
+                       sod_stream_t stream) {
+  SOD_CHECK_ARG(n_query >= 0, "negative size");
+  if (n_query == 0) return SOD_OK;
+  SOD_CHECK_ARG(best && own && runner_up, "null pointer");
+  const int threads = 256;
+  top2_runner_up_kernel<<<static_cast<unsigned>((n_query + threads - 1) / threads), threads, 0,
+                          static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(best), reinterpret_cast<const long long*>(own), n_query,
+      reinterpret_cast<long long*>(runner_up));
+  SOD_CHECK_LAUNCH("top2_runner_up_kernel");
+  return SOD_OK;
+}
+
+int sod_top2_from_keys(const int64_t* best, const int64_t* second, int64_t n_query, int32_t* out_idx,
+                       uint32_t* out_d2, float* out_dist, uint8_t* out_pass, double ratio, sod_stream_t stream) {
+  SOD_CHECK_ARG(n_query >= 0, "negative size");
+  if (n_query == 0) return SOD_OK;
+  SOD_CHECK_ARG(best && second && out_idx && out_d2, "null pointer");
+  const int threads = 256;
+  top2_from_keys_kernel<<<static_cast<unsigned>((n_query + threads - 1) / threads), threads, 0,
+                          static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(best), reinterpret_cast<const long long*>(second), n_query, out_idx,
+      out_d2, out_dist, out_pass, ratio);
+  SOD_CHECK_LAUNCH("top2_from_keys_kernel");
   return SOD_OK;
 }
 

@@ -157,6 +157,30 @@ def merge_top2(parts_idx: torch.Tensor, parts_d2: torch.Tensor, ratio: float = R
     return idx, d2, dist, ok
 
 
+def allreduce_merge_top2(idx: torch.Tensor, d2: torch.Tensor, all_reduce_min, ratio: float = RATIO):
+    """Shard merge as two MIN reductions over packed (d2, row) keys (include/sod.h, K3 collective
+    form): this rank's lists [nq,2] -> the global (idx, d2, dist, pass).  `all_reduce_min(t)` reduces
+    an int64 tensor in place with MIN over the ranks that hold the other shards
+    (torch.distributed.all_reduce with ReduceOp.MIN)."""
+    idx = _require_cuda(idx, torch.int32, "idx")
+    d2 = _require_cuda(d2, torch.int32, "d2")
+    nq, dev = int(idx.shape[0]), idx.device
+    own = torch.empty((2, nq), dtype=torch.int64, device=dev)
+    best = torch.empty(nq, dtype=torch.int64, device=dev)
+    check(lib.sod_top2_keys(_ptr(idx), _ptr(d2), nq, _ptr(own), _ptr(best), _stream()), "sod_top2_keys")
+    all_reduce_min(best)
+    second = torch.empty(nq, dtype=torch.int64, device=dev)
+    check(lib.sod_top2_runner_up(_ptr(best), _ptr(own), nq, _ptr(second), _stream()), "sod_top2_runner_up")
+    all_reduce_min(second)
+    out_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    out_d2 = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    ok = torch.empty(nq, dtype=torch.uint8, device=dev)
+    check(lib.sod_top2_from_keys(_ptr(best), _ptr(second), nq, _ptr(out_idx), _ptr(out_d2), _ptr(dist), _ptr(ok),
+                                 float(ratio), _stream()), "sod_top2_from_keys")
+    return out_idx, out_d2, dist, ok
+
+
 def knn_match_ratio(q_u8: torch.Tensor, matcher: Matcher, ratio: float = RATIO):
     """Single-shard convenience: knnMatch(k=2) + ratio flags."""
     idx, d2 = matcher.top2(q_u8)

@@ -4,9 +4,11 @@ use; main.Main is the object-level drop-in on top of the same engine.
 
 Multi-GPU: one process per GPU; the database rows are split contiguously and
 object-aligned across ranks, the query batch is replicated, every rank computes shard-local top-2
-with global indices, one all-gather of 16 B per query row exchanges them, sod_top2_merge reproduces
-the single-GPU result (ties included), and each rank runs Hough + affine for the matches of its own
-objects only.  There is no other collective.
+with global indices, and one exchange merges them: two MIN all-reduces over packed (d2, row) keys,
+8 B per query row each (sod_top2_keys / sod_top2_runner_up / sod_top2_from_keys), which reproduces
+the single-GPU result, ties included; the bf16 path all-gathers 16 B per row and merges with
+sod_top2_merge_f32.  Each rank then runs Hough + affine for the matches of its own objects only.
+There is no other collective.
 """
 from __future__ import annotations
 
@@ -28,6 +30,25 @@ def shard_bounds(n_objects: int, rows_per_object: np.ndarray | int, rank: int, w
     return obj_lo, obj_hi, int(starts[obj_lo]), int(starts[obj_hi])
 
 
+SEED_ROWS = 16384          # a sensible size of the optional threshold-seeding sample of a sharded database
+QUERY_BLOCK = 256          # query rows per matcher unit: threshold slices must start on this boundary
+
+
+def seed_sample_rows(n_db_rows: int, n_seed: int = SEED_ROWS) -> np.ndarray:
+    """Row numbers of the seeding sample: an even stride over the WHOLE database (the same on every rank)."""
+    n_seed = min(int(n_seed), int(n_db_rows))
+    return (np.arange(n_seed, dtype=np.int64) * int(n_db_rows)) // max(n_seed, 1)
+
+
+def seed_query_slice(n_query: int, rank: int, world: int) -> tuple[int, int]:
+    """The query rows whose thresholds `rank` establishes on the seeding sample: whole matcher blocks,
+    split evenly; the slices of all ranks tile [0, n_query)."""
+    blocks = (int(n_query) + QUERY_BLOCK - 1) // QUERY_BLOCK
+    lo = blocks * rank // world * QUERY_BLOCK
+    hi = blocks * (rank + 1) // world * QUERY_BLOCK
+    return min(lo, int(n_query)), min(hi, int(n_query))
+
+
 @dataclass
 class ModelDatabase:
     """Host-side description of the model database (what GenerateDatabaseInfo pickles, as arrays)."""
@@ -44,10 +65,13 @@ class DetectionPipeline:
     def __init__(self, db: ModelDatabase, max_queries: int, frame_wh: np.ndarray, rank: int = 0,
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
                  affine_threshold: int = 4, per_object_spaces: bool = True, device: str | torch.device = "cuda",
-                 shard: str = "db"):
-        """shard="db": database rows split over the ranks, one all-gather of top-2.
+                 shard: str = "db", seed_rows: int = 0):
+        """shard="db": database rows split over the ranks, one exchange of the shard-local top-2.
         shard="frames": database replicated on every rank, the caller gives each rank its own frames
-        (no collective at all); the pipeline then behaves exactly like a single-GPU one."""
+        (no collective at all); the pipeline then behaves exactly like a single-GPU one.
+        seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
+        seeds the pruning thresholds (see detect_device).  Off by default: measured on B200 it saves
+        less than its own sweep and the sharing kernel instance cost."""
         if shard not in ("db", "frames"):
             raise ValueError("shard must be 'db' or 'frames'")
         self.shard_mode = shard
@@ -68,18 +92,21 @@ class DetectionPipeline:
         # u8 descriptors (what OpenCV SIFT produces) take the exact kind::i8 matcher; float32 descriptors
         # the bf16 path with its stated tolerance (include/sod.h) - queries must then be float32 too.
         self.float_path = des_dev.dtype == torch.float32
-        self.seed_tiles = 0
+        self.seed_matcher = None
         if self.float_path:
             self.shard = E.prepare_db_float(des_dev, index_base=self.row_lo)
             self.matcher = E.FloatMatcher(self.shard)
         else:
             self.shard = E.prepare_db(des_dev, index_base=self.row_lo)
             self.matcher = E.Matcher(self.shard)
-            # database-sharded runs sweep this many stored tiles before the ranks exchange thresholds
-            # (the decision must be the same on every rank: it depends on the whole database only)
-            n_tiles = self.matcher.n_tiles
-            if world > 1 and len(image) // world >= 64 * 128:
-                self.seed_tiles = min(max(16, n_tiles // 8), n_tiles)
+            # Database-sharded runs keep a small even sample of the WHOLE database on every rank; it only
+            # seeds pruning thresholds (detect_device).  The choice depends on the whole database and on
+            # the argument alone, so it is the same on every rank.
+            if world > 1 and seed_rows > 0:
+                rows = seed_sample_rows(len(image), seed_rows)
+                sample = db.des[torch.from_numpy(rows)] if isinstance(db.des, torch.Tensor) else \
+                    torch.from_numpy(np.ascontiguousarray(np.asarray(db.des)[rows]))
+                self.seed_matcher = E.Matcher(E.prepare_db(sample.to(self.device).contiguous(), index_base=0))
         self.max_queries = int(max_queries)
         nq = self.max_queries
         dev = self.device
@@ -99,13 +126,14 @@ class DetectionPipeline:
         self._copy_stream = None
         self._loaded = [None, None]      # event: the set's host->device copies have landed
         self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
-        if world > 1:
+        if world > 1 and self.float_path:   # the bf16 path exchanges by all-gather (float distances)
             self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
-            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32 if self.float_path else torch.int32,
-                                          device=dev)
-        # our kernels per detect_device call; the sample sweep of a database-sharded run adds
-        # one match launch and two list merges
-        self.launches_per_call = 16 + (3 if self.seed_tiles else 0)
+            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32, device=dev)
+        # our kernels per detect_device call; the key exchange of a database-sharded run is
+        # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
+        # match launch and its list merge
+        self.launches_per_call = 16 + (2 if world > 1 and not self.float_path else 0) + \
+            (3 if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
     def _qset(self, slot: int) -> dict:
@@ -149,32 +177,39 @@ class DetectionPipeline:
                                                                     qs["frame"])
         q = self.q_des[:n]
         merge = E.merge_top2_float if self.float_path else E.merge_top2
-        if self.world > 1 and not self.float_path and self.seed_tiles > 0:
-            # Two sweeps per shard with one exchange in between: every rank first sweeps a sample of its
-            # shard (the first stored tiles: an even sample of the norm range), the ranks min-reduce the
-            # rows' 2nd-best bounds (4 B per query row), and the rest of each shard is swept with the
-            # GLOBAL bound from its first tile on.  Without this every shard re-establishes its own
-            # thresholds, which costs ~2 ln(n) slow-path updates per row and shard.
+        if self.seed_matcher is not None:
+            # Threshold seeding.  A shard-local sweep has to establish every query row's pruning threshold
+            # from scratch - about 2 ln(rows) slow-path updates per row and SHARD, i.e. G times the
+            # threshold work of one GPU holding the whole database.  Instead every rank sweeps the small
+            # replicated sample of the whole database for 1/G of the query rows only, the ranks min-reduce
+            # the thresholds (4 B per query row), and each rank sweeps its shard with the bound of a global
+            # sample from its first tile on.  The sample's rows are database rows, so its 2nd best is an
+            # upper bound of the final 2nd best and pruning with it is exact (ties pass); the sample's own
+            # candidate lists are dropped - every sample row is found again by the rank that owns it.
             import torch.distributed as dist
-            m = self.matcher
-            thr = m.new_thresholds(n)
-            i1, d1 = m.top2(q, (0, self.seed_tiles), thr)
+            thr = self.matcher.new_thresholds(n)
+            s_lo, s_hi = seed_query_slice(n, self.rank, self.world)
+            if s_hi > s_lo:
+                self.seed_matcher.top2(q[s_lo:s_hi], None, thr[s_lo:])
             dist.all_reduce(thr, op=dist.ReduceOp.MIN, group=self.group)
-            i2, d2b = m.top2(q, (self.seed_tiles, m.n_tiles), thr, prepared=True)
-            idx, d2 = E.merge_top2(torch.stack([i1, i2]), torch.stack([d1, d2b]))[:2]
+            idx, d2 = self.matcher.top2(q, None, thr)
         else:
             idx, d2 = self.matcher.top2(q)
-        if self.world > 1:
+        if self.world > 1 and not self.float_path:
+            # The exchange: candidates as signed 64-bit keys (d2 << 32 | global row) whose MIN
+            # over the ranks is the merged best, so two MIN all-reduces of 8 B per query row - reduced
+            # inside the switch on NVSwitch - replace gathering G lists of 16 B per row onto every rank.
+            import torch.distributed as dist
+            idx, d2, dist_f, ok = E.allreduce_merge_top2(
+                idx, d2, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group))
+        elif self.world > 1:
             import torch.distributed as dist
             gi, gd = self._gather_idx[:, :n], self._gather_d2[:, :n]
-            if n == self.max_queries:
-                dist.all_gather_into_tensor(gi, idx, group=self.group)
-                dist.all_gather_into_tensor(gd, d2, group=self.group)
-            else:
+            if n != self.max_queries:
                 gi = torch.empty((self.world, n, 2), dtype=torch.int32, device=self.device)
                 gd = torch.empty((self.world, n, 2), dtype=d2.dtype, device=self.device)
-                dist.all_gather_into_tensor(gi, idx, group=self.group)
-                dist.all_gather_into_tensor(gd, d2, group=self.group)
+            dist.all_gather_into_tensor(gi, idx, group=self.group)
+            dist.all_gather_into_tensor(gd, d2, group=self.group)
             idx, d2, dist_f, ok = merge(gi, gd)
         else:
             idx, d2, dist_f, ok = merge(idx[None], d2[None])

@@ -30,6 +30,16 @@ def main():
                        wl["img_centroid"], wl["img_size"])
     q = (wl["q_des"], wl["q_xy"], wl["q_angle"], wl["q_octave"], wl["q_frame"])
     sharded = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev).detect(*q)
+    # the same with threshold seeding forced on (it is automatic only for large databases): a replicated
+    # 1024-row sample, each rank seeds 1/G of the query rows, one min-reduce, then the shard sweep
+    seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024)
+    assert seeded_pipe.seed_matcher is not None
+    seeded = seeded_pipe.detect(*q)
+    for k in ("idx", "ok", "valid_group", "valid_code", "votes", "status", "params"):
+        o1 = np.lexsort((sharded["valid_code"], sharded["valid_group"]))
+        o2 = np.lexsort((seeded["valid_code"], seeded["valid_group"]))
+        a, b = (sharded[k], seeded[k]) if k in ("idx", "ok") else (sharded[k][o1], seeded[k][o2])
+        assert np.array_equal(a, b), f"threshold seeding changed {k}"
     keys = np.stack([sharded["valid_group"], sharded["valid_code"], sharded["votes"], sharded["status"] & 1], 1)
     params = sharded["params"]
     gathered_k = [None] * world

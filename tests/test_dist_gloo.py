@@ -79,6 +79,153 @@ def test_sharded_top2_merge_equals_single_database(tmp_path):
     assert int(r[0]["hi"]) == int(r[1]["lo"]) and int(r[0]["lo"]) == 0 and int(r[1]["hi"]) == len(db)
 
 
+def _key_worker(rank, world, port, out_dir):
+    """The exchange of the u8 path (include/sod.h, K3 collective form) with numpy in the kernels' place."""
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import sod_oracle as O
+    from scenes import sift_like
+    rng = np.random.default_rng(79)
+    db = sift_like(rng, 3 * 200 + 1)
+    q = sift_like(rng, 130)
+    db[7] = db[420] = db[421] = q[0]          # best and runner-up tie across and inside shards
+    db[600] = q[1]                            # rank 2 of 3 holds ONE row only: it is this row's best
+    cuts = [0, 200, 600, 601][:world + 1] if world == 3 else [0, 300, 601]
+    lo, hi = cuts[rank], cuts[rank + 1]
+    idx, d2 = O.knn2(q, db[lo:hi])
+    none = np.iinfo(np.int64).max
+    key = np.where(idx >= 0, (d2.astype(np.int64) << 32) | (idx + lo).astype(np.int64), none)   # sod_top2_keys
+    best = torch.from_numpy(key[:, 0].copy())
+    dist.all_reduce(best, op=dist.ReduceOp.MIN)
+    second = torch.from_numpy(np.where(key[:, 0] == best.numpy(), key[:, 1], key[:, 0]))        # sod_top2_runner_up
+    dist.all_reduce(second, op=dist.ReduceOp.MIN)
+    g = np.stack([best.numpy(), second.numpy()], 1)                                              # sod_top2_from_keys
+    gi = np.where(g != none, g & 0xFFFFFFFF, -1).astype(np.int32)
+    gd = np.where(g != none, g >> 32, -1)
+    np.savez(Path(out_dir) / f"key_rank{rank}.npz", gi=gi, gd=gd)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_min_reduction_of_packed_keys_is_the_merge(tmp_path):
+    """Two MIN all-reduces over (d2 << 32 | row) keys give the single-database top-2: ties resolve to
+    the lowest row, a shard with a single row takes part, every rank ends with the same lists."""
+    world = 3
+    mp.spawn(_key_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import sod_oracle as O
+    from scenes import sift_like
+    rng = np.random.default_rng(79)
+    db = sift_like(rng, 3 * 200 + 1)
+    q = sift_like(rng, 130)
+    db[7] = db[420] = db[421] = q[0]
+    db[600] = q[1]
+    ridx, rd2 = O.knn2(q, db)
+    assert ridx[0].tolist() == [7, 420] and ridx[1, 0] == 600
+    for k in range(world):
+        z = np.load(tmp_path / f"key_rank{k}.npz")
+        np.testing.assert_array_equal(z["gi"], ridx)
+        np.testing.assert_array_equal(z["gd"], rd2)
+
+
+def _pruned_top2(q, shard, lo, thr):
+    """What a shard sweep with carried thresholds may return: rows whose d2 - |q|^2 exceeds the row's
+    threshold are invisible (the kernel prunes them), the rest compete as usual."""
+    from oracle import sod_oracle as O
+    qn = (q.astype(np.int64) ** 2).sum(1)
+    d = ((q[:, None, :].astype(np.int64) - shard[None].astype(np.int64)) ** 2).sum(2)
+    idx = np.full((len(q), 2), -1, np.int32)
+    d2 = np.full((len(q), 2), -1, np.int64)
+    for r in range(len(q)):
+        cand = np.flatnonzero(d[r] - qn[r] <= thr[r])
+        order = cand[np.lexsort((cand, d[r, cand]))][:2]
+        idx[r, :len(order)] = order + lo
+        d2[r, :len(order)] = d[r, order]
+    return idx, d2
+
+
+def _seed_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import sod_oracle as O
+    from scenes import sift_like
+    from sod_b200.pipeline import seed_query_slice, seed_sample_rows, shard_bounds
+
+    rng = np.random.default_rng(78)
+    rows_per = np.array([300, 120, 50, 400, 90, 210, 33])
+    db = sift_like(rng, int(rows_per.sum()))
+    q = sift_like(rng, 700)
+    db[5] = db[900] = q[0]
+    q[2:60] = np.clip(db[rng.integers(0, len(db), 58)].astype(np.int16) + rng.integers(-3, 4, (58, 128)), 0, 255).astype(np.uint8)
+    _, _, lo, hi = shard_bounds(len(rows_per), rows_per, rank, world)
+    # seeding: this rank's query slice against the replicated sample -> 2nd-best bound, "none" elsewhere
+    none = 0x7F7F7F7F
+    thr = torch.full((len(q),), none, dtype=torch.int32)
+    sample = db[seed_sample_rows(len(db), 64)]
+    s_lo, s_hi = seed_query_slice(len(q), rank, world)
+    _, sd2 = O.knn2(q[s_lo:s_hi], sample)
+    qn = (q.astype(np.int64) ** 2).sum(1)
+    thr[s_lo:s_hi] = torch.from_numpy((sd2[:, 1] - qn[s_lo:s_hi]).astype(np.int32))
+    dist.all_reduce(thr, op=dist.ReduceOp.MIN)
+    assert int((thr == none).sum()) == 0                                      # the slices tile the batch
+    idx, d2 = _pruned_top2(q, db[lo:hi], lo, thr.numpy().astype(np.int64))
+    mine = torch.from_numpy(np.stack([idx, d2.astype(np.int32)], 0))
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    parts = torch.stack(gathered).numpy()
+    gi, gd = O.merge_top2(parts[:, 0], parts[:, 1].astype(np.int64))
+    np.savez(Path(out_dir) / f"seed_rank{rank}.npz", gi=gi, gd=gd, pruned=int((idx < 0).sum()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_threshold_seeding_keeps_the_sharded_result_exact(tmp_path):
+    """Every rank seeds 1/G of the query rows on a replicated sample of the whole database, one
+    min-reduce spreads the bounds, the shard sweeps prune with them: the merged top-2 is still the
+    single-database result, ties included (host logic of DetectionPipeline.detect_device)."""
+    world = 2
+    mp.spawn(_seed_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import sod_oracle as O
+    from scenes import sift_like
+    rng = np.random.default_rng(78)
+    rows_per = np.array([300, 120, 50, 400, 90, 210, 33])
+    db = sift_like(rng, int(rows_per.sum()))
+    q = sift_like(rng, 700)
+    db[5] = db[900] = q[0]
+    q[2:60] = np.clip(db[rng.integers(0, len(db), 58)].astype(np.int16) + rng.integers(-3, 4, (58, 128)), 0, 255).astype(np.uint8)
+    ridx, rd2 = O.knn2(q, db)
+    for k in range(world):
+        z = np.load(tmp_path / f"seed_rank{k}.npz")
+        np.testing.assert_array_equal(z["gi"], ridx)
+        np.testing.assert_array_equal(z["gd"], rd2)
+        assert int(z["pruned"]) > 0                          # the bound did hide shard-local candidates
+
+
+def test_seed_slices_and_sample():
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    from sod_b200.pipeline import QUERY_BLOCK, seed_query_slice, seed_sample_rows
+    for n in (0, 1, 255, 256, 257, 5000, 1_280_000):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for rank in range(world):
+                lo, hi = seed_query_slice(n, rank, world)
+                assert lo == prev and lo % QUERY_BLOCK == 0 or lo == n
+                prev = hi
+            assert prev == n
+    rows = seed_sample_rows(1_000_000, 16384)
+    assert len(rows) == 16384 and rows[0] == 0 and rows[-1] < 1_000_000 and np.all(np.diff(rows) > 0)
+    assert seed_sample_rows(10, 64).tolist() == list(range(10))
+
+
 def test_shard_bounds_are_object_aligned_and_cover():
     sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
     from sod_b200.pipeline import shard_bounds
