@@ -309,7 +309,8 @@ def run_ours(args):
         for k in ("q_xy", "q_angle", "q_octave", "q_frame", "q_des"):
             wl[k] = wl[k][lo:hi]
         nq = hi - lo
-    pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=device, shard=args.shard)
+    pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=device, shard=args.shard,
+                             exchange=args.exchange)
     host = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).pin_memory()
             for k in ("q_xy", "q_angle", "q_octave", "q_frame")}
     host["q_des"] = wl["q_des"].cpu().pin_memory()
@@ -415,7 +416,7 @@ def run_ours(args):
             "config": {"workload": (f"{args.frames} frames x {args.per_frame} query descriptors vs {args.objects} objects x "
                                     f"{args.kp_per_object} = {ndb} database descriptors (BASELINE configs[3])"),
                        "n_query": nq_total, "n_db": ndb, "bins": 15, "ratio": 0.75, "hough_spaces": "per (frame, object)",
-                       "parallelism": ("single" if world == 1 else f"db-shard{world}+allgather-top2" if args.shard == "db"
+                       "parallelism": ("single" if world == 1 else f"db-shard{world}+{args.exchange}-top2" if args.shard == "db"
                                        else f"frame-shard{world}, database replicated, no collective"),
                        "l2": "inputs larger than L2 (128 MB database + 164 MB queries per step)"},
             "e2e": {"value": nq_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -493,6 +494,8 @@ def main():
     ap.add_argument("--shard", default="frames", choices=["db", "frames"],
                     help="N > 1: split the frames (default: database replicated, no collective) or the database "
                          "rows (one NCCL all-gather of the shard-local top-2)")
+    ap.add_argument("--exchange", default="scatter", choices=["scatter", "gather"],
+                    help="--shard db: how the shard-local top-2 are merged (DetectionPipeline)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

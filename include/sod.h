@@ -105,24 +105,24 @@ int sod_top2_merge(const int32_t* parts_idx, const uint32_t* parts_d2, int32_t n
                    int64_t n_query, int32_t* out_idx, uint32_t* out_d2, float* out_dist,
                    uint8_t* out_pass, double ratio, sod_stream_t stream);
 
-/* K3 in collective form, for a database sharded over several GPUs (the shard merge the
- * north star describes as "an NCCL all-gather over NVLink merges them").  A candidate is one signed
- * 64-bit key (d2 << 32 | global row; INT64_MAX = none), whose order is the merge order (distance, then
- * lowest index - cv2's tie rule).  The MIN over the ranks of every row's best key IS the merged best,
- * so one MIN all-reduce of 8 B per query row (reduced inside the switch on NVSwitch) replaces the
- * gather of every rank's lists; the rank that owns the best then offers its own 2nd, all others their
- * 1st, and a second MIN all-reduce yields the merged 2nd (a database row lives on exactly one rank):
- *   sod_top2_keys      idx/d2 [n_query][2] of this rank -> own int64 [2][n_query], best = copy of own[0]
- *   (caller)           all-reduce MIN over best
- *   sod_top2_runner_up runner_up[i] = own[0][i] == best[i] ? own[1][i] : own[0][i]
- *   (caller)           all-reduce MIN over runner_up
- *   sod_top2_from_keys keys -> out_idx/out_d2/out_dist/out_pass exactly as sod_top2_merge writes them. */
-int sod_top2_keys(const int32_t* idx, const uint32_t* d2, int64_t n_query, int64_t* own, int64_t* best,
+/* K3 in exchange form, for a database sharded over G GPUs (the shard merge the north
+ * star describes as "an NCCL all-gather over NVLink merges them").  A candidate is one signed 64-bit
+ * key (d2 << 32 | global row; INT64_MAX = none) whose order is the merge order (distance, then lowest
+ * index - cv2's tie rule); keys travel as [row][2] pairs.  Instead of gathering every rank's lists onto
+ * every rank (G x 16 B per query row received), rank r merges only rows [r*S, (r+1)*S), S = rows / G:
+ *   sod_top2_keys        idx/d2 [n_query][2] of this rank -> keys int64 [n_rows][2]; rows n_query..n_rows
+ *                        (padding up to G whole slices) are "none"
+ *   (caller)             all-to-all: slice r of every rank's keys goes to rank r (16 B per row and peer)
+ *   sod_top2_merge_keys  parts int64 [n_parts][n_rows][2] -> the two smallest keys per row, [n_rows][2]
+ *   (caller)             all-gather of the merged slices (16 B per query row)
+ *   sod_top2_from_keys   keys [n_query][2] -> out_idx/out_d2/out_dist/out_pass exactly as
+ *                        sod_top2_merge writes them (ratio test included).
+ * Key arrays must be 16-byte aligned. */
+int sod_top2_keys(const int32_t* idx, const uint32_t* d2, int64_t n_query, int64_t n_rows, int64_t* keys,
                   sod_stream_t stream);
-int sod_top2_runner_up(const int64_t* best, const int64_t* own, int64_t n_query, int64_t* runner_up,
-                       sod_stream_t stream);
-int sod_top2_from_keys(const int64_t* best, const int64_t* second, int64_t n_query, int32_t* out_idx,
-                       uint32_t* out_d2, float* out_dist, uint8_t* out_pass, double ratio, sod_stream_t stream);
+int sod_top2_merge_keys(const int64_t* parts, int32_t n_parts, int64_t n_rows, int64_t* out, sod_stream_t stream);
+int sod_top2_from_keys(const int64_t* keys, int64_t n_query, int32_t* out_idx, uint32_t* out_d2, float* out_dist,
+                       uint8_t* out_pass, double ratio, sod_stream_t stream);
 
 /* ---- bf16 fallback for descriptors that are NOT integer-valued 0..255 (non-OpenCV extractors,
  * normalised float descriptors).  Same reference call as sod_match_top2 (main.py:70-73), approximate

@@ -553,45 +553,56 @@ __global__ void top2_merge_kernel(const int32_t* __restrict__ parts_idx,
   write_top2_row(row, i1, d1, i2, d2, out_idx, out_d2, out_dist, out_pass, ratio);
 }
 
-// K3, collective form.  A candidate as one signed 64-bit key (d2 << 32 | global row): signed order is
-// the (distance, index) order of the merge, so the MIN of the ranks' keys IS the merged best - an
-// all-reduce (in-switch on NVSwitch) replaces gathering every rank's lists.  No entry: kNoneKey.
+// K3, exchange form.  A candidate as one signed 64-bit key (d2 << 32 | global row): signed order is the
+// (distance, index) order of the merge.  No entry: kNoneKey.  Keys travel as [row][2] pairs, so a
+// contiguous range of query rows is a contiguous message.
 constexpr long long kNoneKey = 0x7FFFFFFFFFFFFFFFll;
 
 __global__ void top2_keys_kernel(const int32_t* __restrict__ idx, const uint32_t* __restrict__ d2, int64_t nq,
-                                 long long* __restrict__ own, long long* __restrict__ best) {
+                                 int64_t n_rows, longlong2* __restrict__ keys) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (row >= nq) return;
-  const int2 ci = *reinterpret_cast<const int2*>(idx + row * 2);
-  const uint2 cd = *reinterpret_cast<const uint2*>(d2 + row * 2);
-  const long long k1 = ci.x < 0 ? kNoneKey : (static_cast<long long>(cd.x) << 32) | static_cast<uint32_t>(ci.x);
-  const long long k2 = ci.y < 0 ? kNoneKey : (static_cast<long long>(cd.y) << 32) | static_cast<uint32_t>(ci.y);
-  own[row] = k1;
-  own[nq + row] = k2;
-  best[row] = k1;
+  if (row >= n_rows) return;
+  longlong2 k = make_longlong2(kNoneKey, kNoneKey);  // rows past nq: padding up to a whole number of slices
+  if (row < nq) {
+    const int2 ci = *reinterpret_cast<const int2*>(idx + row * 2);
+    const uint2 cd = *reinterpret_cast<const uint2*>(d2 + row * 2);
+    if (ci.x >= 0) k.x = (static_cast<long long>(cd.x) << 32) | static_cast<uint32_t>(ci.x);
+    if (ci.y >= 0) k.y = (static_cast<long long>(cd.y) << 32) | static_cast<uint32_t>(ci.y);
+  }
+  keys[row] = k;
 }
 
-// After best = MIN over ranks: the rank that owns the global best offers its own 2nd, every other rank
-// its 1st; the MIN of these is the global 2nd (database rows live on exactly one rank).
-__global__ void top2_runner_up_kernel(const long long* __restrict__ best, const long long* __restrict__ own,
-                                      int64_t nq, long long* __restrict__ runner_up) {
+// n_parts lists of key pairs for the same rows -> the two smallest keys per row (keys of different
+// database rows differ, so there is nothing to de-duplicate).
+__global__ void top2_merge_keys_kernel(const longlong2* __restrict__ parts, int n_parts, int64_t n_rows,
+                                       longlong2* __restrict__ out) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (row >= nq) return;
-  const long long k1 = own[row];
-  runner_up[row] = k1 == best[row] ? own[nq + row] : k1;
+  if (row >= n_rows) return;
+  long long k1 = kNoneKey, k2 = kNoneKey;
+  for (int p = 0; p < n_parts; ++p) {
+    const longlong2 c = parts[static_cast<int64_t>(p) * n_rows + row];
+    // c.x <= c.y: at most c.x and c.y enter, in this order
+    if (c.x < k1) {
+      k2 = min(k1, c.y);
+      k1 = c.x;
+    } else if (c.x < k2) {
+      k2 = c.x;
+    }
+  }
+  out[row] = make_longlong2(k1, k2);
 }
 
-__global__ void top2_from_keys_kernel(const long long* __restrict__ best, const long long* __restrict__ second,
-                                      int64_t nq, int32_t* __restrict__ out_idx, uint32_t* __restrict__ out_d2,
+__global__ void top2_from_keys_kernel(const longlong2* __restrict__ keys, int64_t nq,
+                                      int32_t* __restrict__ out_idx, uint32_t* __restrict__ out_d2,
                                       float* __restrict__ out_dist, uint8_t* __restrict__ out_pass, double ratio) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (row >= nq) return;
-  const long long k1 = best[row], k2 = second[row];
-  const bool h1 = k1 != kNoneKey, h2 = k2 != kNoneKey;
-  write_top2_row(row, h1 ? static_cast<int32_t>(k1 & 0xFFFFFFFFll) : -1,
-                 h1 ? static_cast<uint32_t>(k1 >> 32) : 0xFFFFFFFFu,
-                 h2 ? static_cast<int32_t>(k2 & 0xFFFFFFFFll) : -1,
-                 h2 ? static_cast<uint32_t>(k2 >> 32) : 0xFFFFFFFFu, out_idx, out_d2, out_dist, out_pass, ratio);
+  const longlong2 k = keys[row];
+  const bool h1 = k.x != kNoneKey, h2 = k.y != kNoneKey;
+  write_top2_row(row, h1 ? static_cast<int32_t>(k.x & 0xFFFFFFFFll) : -1,
+                 h1 ? static_cast<uint32_t>(k.x >> 32) : 0xFFFFFFFFu,
+                 h2 ? static_cast<int32_t>(k.y & 0xFFFFFFFFll) : -1,
+                 h2 ? static_cast<uint32_t>(k.y >> 32) : 0xFFFFFFFFu, out_idx, out_d2, out_dist, out_pass, ratio);
 }
 
 struct Plan {
@@ -815,43 +826,44 @@ int sod_top2_merge(const int32_t* parts_idx, const uint32_t* parts_d2, int32_t n
   return SOD_OK;
 }
 
-int sod_top2_keys(const int32_t* idx, const uint32_t* d2, int64_t n_query, int64_t* own, int64_t* best,
+int sod_top2_keys(const int32_t* idx, const uint32_t* d2, int64_t n_query, int64_t n_rows, int64_t* keys,
                   sod_stream_t stream) {
-  SOD_CHECK_ARG(n_query >= 0, "negative size");
-  if (n_query == 0) return SOD_OK;
-  SOD_CHECK_ARG(idx && d2 && own && best, "null pointer");
+  SOD_CHECK_ARG(n_query >= 0 && n_rows >= n_query, "need 0 <= n_query <= n_rows");
+  if (n_rows == 0) return SOD_OK;
+  SOD_CHECK_ARG(keys && (n_query == 0 || (idx && d2)), "null pointer");
+  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(keys) & 15) == 0, "keys must be 16-byte aligned");
   const int threads = 256;
-  top2_keys_kernel<<<static_cast<unsigned>((n_query + threads - 1) / threads), threads, 0,
-                     static_cast<cudaStream_t>(stream)>>>(idx, d2, n_query, reinterpret_cast<long long*>(own),
-                                                          reinterpret_cast<long long*>(best));
+  top2_keys_kernel<<<static_cast<unsigned>((n_rows + threads - 1) / threads), threads, 0,
+                     static_cast<cudaStream_t>(stream)>>>(idx, d2, n_query, n_rows,
+                                                          reinterpret_cast<longlong2*>(keys));
   SOD_CHECK_LAUNCH("top2_keys_kernel");
   return SOD_OK;
 }
 
-int sod_top2_runner_up(const int64_t* best, const int64_t* own, int64_t n_query, int64_t* runner_up,
-                       sod_stream_t stream) {
-  SOD_CHECK_ARG(n_query >= 0, "negative size");
-  if (n_query == 0) return SOD_OK;
-  SOD_CHECK_ARG(best && own && runner_up, "null pointer");
+int sod_top2_merge_keys(const int64_t* parts, int32_t n_parts, int64_t n_rows, int64_t* out, sod_stream_t stream) {
+  SOD_CHECK_ARG(n_parts >= 0 && n_rows >= 0, "negative size");
+  if (n_rows == 0) return SOD_OK;
+  SOD_CHECK_ARG(out && (n_parts == 0 || parts), "null pointer");
+  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(parts) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "key arrays must be 16-byte aligned");
   const int threads = 256;
-  top2_runner_up_kernel<<<static_cast<unsigned>((n_query + threads - 1) / threads), threads, 0,
-                          static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(best), reinterpret_cast<const long long*>(own), n_query,
-      reinterpret_cast<long long*>(runner_up));
-  SOD_CHECK_LAUNCH("top2_runner_up_kernel");
+  top2_merge_keys_kernel<<<static_cast<unsigned>((n_rows + threads - 1) / threads), threads, 0,
+                           static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const longlong2*>(parts), n_parts,
+                                                                n_rows, reinterpret_cast<longlong2*>(out));
+  SOD_CHECK_LAUNCH("top2_merge_keys_kernel");
   return SOD_OK;
 }
 
-int sod_top2_from_keys(const int64_t* best, const int64_t* second, int64_t n_query, int32_t* out_idx,
-                       uint32_t* out_d2, float* out_dist, uint8_t* out_pass, double ratio, sod_stream_t stream) {
+int sod_top2_from_keys(const int64_t* keys, int64_t n_query, int32_t* out_idx, uint32_t* out_d2, float* out_dist,
+                       uint8_t* out_pass, double ratio, sod_stream_t stream) {
   SOD_CHECK_ARG(n_query >= 0, "negative size");
   if (n_query == 0) return SOD_OK;
-  SOD_CHECK_ARG(best && second && out_idx && out_d2, "null pointer");
+  SOD_CHECK_ARG(keys && out_idx && out_d2, "null pointer");
+  SOD_CHECK_ARG((reinterpret_cast<uintptr_t>(keys) & 15) == 0, "keys must be 16-byte aligned");
   const int threads = 256;
   top2_from_keys_kernel<<<static_cast<unsigned>((n_query + threads - 1) / threads), threads, 0,
-                          static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(best), reinterpret_cast<const long long*>(second), n_query, out_idx,
-      out_d2, out_dist, out_pass, ratio);
+                          static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const longlong2*>(keys), n_query,
+                                                               out_idx, out_d2, out_dist, out_pass, ratio);
   SOD_CHECK_LAUNCH("top2_from_keys_kernel");
   return SOD_OK;
 }

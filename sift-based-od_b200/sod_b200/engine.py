@@ -157,28 +157,55 @@ def merge_top2(parts_idx: torch.Tensor, parts_d2: torch.Tensor, ratio: float = R
     return idx, d2, dist, ok
 
 
-def allreduce_merge_top2(idx: torch.Tensor, d2: torch.Tensor, all_reduce_min, ratio: float = RATIO):
-    """Shard merge as two MIN reductions over packed (d2, row) keys (include/sod.h, K3 collective
-    form): this rank's lists [nq,2] -> the global (idx, d2, dist, pass).  `all_reduce_min(t)` reduces
-    an int64 tensor in place with MIN over the ranks that hold the other shards
-    (torch.distributed.all_reduce with ReduceOp.MIN)."""
+def top2_keys(idx: torch.Tensor, d2: torch.Tensor, n_rows: int | None = None) -> torch.Tensor:
+    """This rank's lists [nq,2] -> packed keys int64 [n_rows,2] (rows past nq: none)."""
     idx = _require_cuda(idx, torch.int32, "idx")
     d2 = _require_cuda(d2, torch.int32, "d2")
-    nq, dev = int(idx.shape[0]), idx.device
-    own = torch.empty((2, nq), dtype=torch.int64, device=dev)
-    best = torch.empty(nq, dtype=torch.int64, device=dev)
-    check(lib.sod_top2_keys(_ptr(idx), _ptr(d2), nq, _ptr(own), _ptr(best), _stream()), "sod_top2_keys")
-    all_reduce_min(best)
-    second = torch.empty(nq, dtype=torch.int64, device=dev)
-    check(lib.sod_top2_runner_up(_ptr(best), _ptr(own), nq, _ptr(second), _stream()), "sod_top2_runner_up")
-    all_reduce_min(second)
-    out_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
-    out_d2 = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    nq = int(idx.shape[0])
+    n_rows = nq if n_rows is None else int(n_rows)
+    keys = torch.empty((n_rows, 2), dtype=torch.int64, device=idx.device)
+    check(lib.sod_top2_keys(_ptr(idx), _ptr(d2), nq, n_rows, _ptr(keys), _stream()), "sod_top2_keys")
+    return keys
+
+
+def merge_keys(parts: torch.Tensor) -> torch.Tensor:
+    """Key lists int64 [G,rows,2] -> the two smallest keys per row, [rows,2]."""
+    parts = _require_cuda(parts, torch.int64, "parts")
+    g, rows = int(parts.shape[0]), int(parts.shape[1])
+    out = torch.empty((rows, 2), dtype=torch.int64, device=parts.device)
+    check(lib.sod_top2_merge_keys(_ptr(parts), g, rows, _ptr(out), _stream()), "sod_top2_merge_keys")
+    return out
+
+
+def top2_from_keys(keys: torch.Tensor, nq: int, ratio: float = RATIO):
+    """Merged keys int64 [>=nq,2] -> (idx [nq,2], d2 [nq,2], dist f32 [nq,2], pass u8 [nq])."""
+    keys = _require_cuda(keys, torch.int64, "keys")
+    dev = keys.device
+    idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+    d2 = torch.empty((nq, 2), dtype=torch.int32, device=dev)
     dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
     ok = torch.empty(nq, dtype=torch.uint8, device=dev)
-    check(lib.sod_top2_from_keys(_ptr(best), _ptr(second), nq, _ptr(out_idx), _ptr(out_d2), _ptr(dist), _ptr(ok),
-                                 float(ratio), _stream()), "sod_top2_from_keys")
-    return out_idx, out_d2, dist, ok
+    check(lib.sod_top2_from_keys(_ptr(keys), nq, _ptr(idx), _ptr(d2), _ptr(dist), _ptr(ok), float(ratio),
+                                 _stream()), "sod_top2_from_keys")
+    return idx, d2, dist, ok
+
+
+def exchange_merge_top2(idx: torch.Tensor, d2: torch.Tensor, world: int, all_to_all, all_gather,
+                        ratio: float = RATIO):
+    """Shard merge in exchange form (include/sod.h, K3): this rank's lists [nq,2] -> the global
+    (idx, d2, dist, pass) on every rank.  all_to_all(out, inp) and all_gather(out, inp) are the
+    collectives over the ranks that hold the other shards (torch.distributed.all_to_all_single /
+    all_gather_into_tensor): slice r of every rank's keys goes to rank r, which merges its slice of the
+    query rows; the merged slices are gathered.  16 B per query row each way instead of G x 16 B."""
+    nq = int(idx.shape[0])
+    per = (nq + world - 1) // world
+    keys = top2_keys(idx, d2, per * world)                       # [world * per, 2]
+    parts = torch.empty_like(keys)
+    all_to_all(parts, keys)                                      # [world][per][2]: everyone's slice `rank`
+    mine = merge_keys(parts.view(world, per, 2))
+    merged = torch.empty_like(keys)
+    all_gather(merged, mine)
+    return top2_from_keys(merged, nq, ratio)
 
 
 def knn_match_ratio(q_u8: torch.Tensor, matcher: Matcher, ratio: float = RATIO):

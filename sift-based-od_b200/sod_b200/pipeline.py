@@ -4,10 +4,11 @@ use; main.Main is the object-level drop-in on top of the same engine.
 
 Multi-GPU: one process per GPU; the database rows are split contiguously and
 object-aligned across ranks, the query batch is replicated, every rank computes shard-local top-2
-with global indices, and one exchange merges them: two MIN all-reduces over packed (d2, row) keys,
-8 B per query row each (sod_top2_keys / sod_top2_runner_up / sod_top2_from_keys), which reproduces
-the single-GPU result, ties included; the bf16 path all-gathers 16 B per row and merges with
-sod_top2_merge_f32.  Each rank then runs Hough + affine for the matches of its own objects only.
+with global indices, and one exchange merges them: packed (d2, row) keys go to the rank that merges
+their slice of the query rows (all-to-all), the merged slices are gathered (sod_top2_keys /
+sod_top2_merge_keys / sod_top2_from_keys) - or, exchange="gather", every rank gathers all lists and
+merges them itself (sod_top2_merge); both reproduce the single-GPU result, ties included.  The bf16
+path uses the gather form with sod_top2_merge_f32.  Each rank then runs Hough + affine for the matches of its own objects only.
 There is no other collective.
 """
 from __future__ import annotations
@@ -65,15 +66,20 @@ class DetectionPipeline:
     def __init__(self, db: ModelDatabase, max_queries: int, frame_wh: np.ndarray, rank: int = 0,
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
                  affine_threshold: int = 4, per_object_spaces: bool = True, device: str | torch.device = "cuda",
-                 shard: str = "db", seed_rows: int = 0):
+                 shard: str = "db", seed_rows: int = 0, exchange: str = "scatter"):
         """shard="db": database rows split over the ranks, one exchange of the shard-local top-2.
         shard="frames": database replicated on every rank, the caller gives each rank its own frames
         (no collective at all); the pipeline then behaves exactly like a single-GPU one.
         seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
         seeds the pruning thresholds (see detect_device).  Off by default: measured on B200 it saves
-        less than its own sweep and the sharing kernel instance cost."""
+        less than its own sweep and the sharing kernel instance cost.
+        exchange (shard="db"): "scatter" = all-to-all of packed keys, slice merge, all-gather of the merged
+        slices; "gather" = all-gather of every rank's lists + sod_top2_merge on every rank."""
         if shard not in ("db", "frames"):
             raise ValueError("shard must be 'db' or 'frames'")
+        if exchange not in ("scatter", "gather"):
+            raise ValueError("exchange must be 'scatter' or 'gather'")
+        self.exchange = exchange
         self.shard_mode = shard
         if shard == "frames":
             rank, world = 0, 1
@@ -126,13 +132,14 @@ class DetectionPipeline:
         self._copy_stream = None
         self._loaded = [None, None]      # event: the set's host->device copies have landed
         self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
-        if world > 1 and self.float_path:   # the bf16 path exchanges by all-gather (float distances)
+        if world > 1 and (self.float_path or self.exchange == "gather"):
             self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
-            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32, device=dev)
+            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32 if self.float_path else torch.int32,
+                                          device=dev)
         # our kernels per detect_device call; the key exchange of a database-sharded run is
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
-        self.launches_per_call = 16 + (2 if world > 1 and not self.float_path else 0) + \
+        self.launches_per_call = 16 + (2 if world > 1 and not self.float_path and exchange == "scatter" else 0) + \
             (3 if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
@@ -195,13 +202,15 @@ class DetectionPipeline:
             idx, d2 = self.matcher.top2(q, None, thr)
         else:
             idx, d2 = self.matcher.top2(q)
-        if self.world > 1 and not self.float_path:
-            # The exchange: candidates as signed 64-bit keys (d2 << 32 | global row) whose MIN
-            # over the ranks is the merged best, so two MIN all-reduces of 8 B per query row - reduced
-            # inside the switch on NVSwitch - replace gathering G lists of 16 B per row onto every rank.
+        if self.world > 1 and not self.float_path and self.exchange == "scatter":
+            # The exchange in scatter form: candidates travel as signed 64-bit keys
+            # (d2 << 32 | global row), rank r merges the query rows of slice r from all ranks
+            # (all-to-all), the merged slices are gathered: 2 x 16 B per query row instead of G x 16 B.
             import torch.distributed as dist
-            idx, d2, dist_f, ok = E.allreduce_merge_top2(
-                idx, d2, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group))
+            idx, d2, dist_f, ok = E.exchange_merge_top2(
+                idx, d2, self.world,
+                lambda out, inp: dist.all_to_all_single(out, inp, group=self.group),
+                lambda out, inp: dist.all_gather_into_tensor(out, inp, group=self.group))
         elif self.world > 1:
             import torch.distributed as dist
             gi, gd = self._gather_idx[:, :n], self._gather_d2[:, :n]

@@ -35,11 +35,15 @@ def main():
     seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024)
     assert seeded_pipe.seed_matcher is not None
     seeded = seeded_pipe.detect(*q)
-    for k in ("idx", "ok", "valid_group", "valid_code", "votes", "status", "params"):
-        o1 = np.lexsort((sharded["valid_code"], sharded["valid_group"]))
-        o2 = np.lexsort((seeded["valid_code"], seeded["valid_group"]))
-        a, b = (sharded[k], seeded[k]) if k in ("idx", "ok") else (sharded[k][o1], seeded[k][o2])
-        assert np.array_equal(a, b), f"threshold seeding changed {k}"
+    # and with the gather form of the exchange (all-gather of the lists + merge on every rank)
+    gathered_lists = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,
+                                       exchange="gather").detect(*q)
+    for other, what in ((seeded, "threshold seeding"), (gathered_lists, "the gather exchange")):
+        for k in ("idx", "ok", "valid_group", "valid_code", "votes", "status", "params"):
+            o1 = np.lexsort((sharded["valid_code"], sharded["valid_group"]))
+            o2 = np.lexsort((other["valid_code"], other["valid_group"]))
+            a, b = (sharded[k], other[k]) if k in ("idx", "ok") else (sharded[k][o1], other[k][o2])
+            assert np.array_equal(a, b), f"{what} changed {k}"
     keys = np.stack([sharded["valid_group"], sharded["valid_code"], sharded["votes"], sharded["status"] & 1], 1)
     params = sharded["params"]
     gathered_k = [None] * world

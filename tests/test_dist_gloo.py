@@ -79,31 +79,41 @@ def test_sharded_top2_merge_equals_single_database(tmp_path):
     assert int(r[0]["hi"]) == int(r[1]["lo"]) and int(r[0]["lo"]) == 0 and int(r[1]["hi"]) == len(db)
 
 
+def _np_keys(idx, d2, lo, n_rows):
+    """sod_top2_keys in numpy: [n_rows,2] int64, none = INT64_MAX."""
+    none = np.iinfo(np.int64).max
+    keys = np.full((n_rows, 2), none, np.int64)
+    keys[:len(idx)] = np.where(idx >= 0, (d2.astype(np.int64) << 32) | (idx + lo).astype(np.int64), none)
+    return keys
+
+
 def _key_worker(rank, world, port, out_dir):
-    """The exchange of the u8 path (include/sod.h, K3 collective form) with numpy in the kernels' place."""
+    """The exchange of the u8 path (include/sod.h, K3 exchange form) with numpy in the kernels' place."""
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
-    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import sod_oracle as O
     from scenes import sift_like
     rng = np.random.default_rng(79)
-    db = sift_like(rng, 3 * 200 + 1)
-    q = sift_like(rng, 130)
+    db = sift_like(rng, 601)
+    q = sift_like(rng, 130)                   # 130 rows over 3 ranks: slices of 44 with 2 padding rows
     db[7] = db[420] = db[421] = q[0]          # best and runner-up tie across and inside shards
-    db[600] = q[1]                            # rank 2 of 3 holds ONE row only: it is this row's best
-    cuts = [0, 200, 600, 601][:world + 1] if world == 3 else [0, 300, 601]
+    db[600] = q[1]                            # the last rank holds ONE row only: it is this row's best
+    cuts = [0, 200, 600, 601]
     lo, hi = cuts[rank], cuts[rank + 1]
     idx, d2 = O.knn2(q, db[lo:hi])
+    per = (len(q) + world - 1) // world
+    keys = torch.from_numpy(_np_keys(idx, d2, lo, per * world))                    # sod_top2_keys
+    parts = torch.empty_like(keys)
+    dist.all_to_all_single(parts, keys)
+    p = np.sort(parts.numpy().reshape(world, per, 2).transpose(1, 0, 2).reshape(per, -1), axis=1)[:, :2]
+    mine = torch.from_numpy(np.ascontiguousarray(p))                               # sod_top2_merge_keys
+    merged = torch.empty_like(keys)
+    dist.all_gather_into_tensor(merged, mine)
+    g = merged.numpy()[:len(q)]                                                    # sod_top2_from_keys
     none = np.iinfo(np.int64).max
-    key = np.where(idx >= 0, (d2.astype(np.int64) << 32) | (idx + lo).astype(np.int64), none)   # sod_top2_keys
-    best = torch.from_numpy(key[:, 0].copy())
-    dist.all_reduce(best, op=dist.ReduceOp.MIN)
-    second = torch.from_numpy(np.where(key[:, 0] == best.numpy(), key[:, 1], key[:, 0]))        # sod_top2_runner_up
-    dist.all_reduce(second, op=dist.ReduceOp.MIN)
-    g = np.stack([best.numpy(), second.numpy()], 1)                                              # sod_top2_from_keys
     gi = np.where(g != none, g & 0xFFFFFFFF, -1).astype(np.int32)
     gd = np.where(g != none, g >> 32, -1)
     np.savez(Path(out_dir) / f"key_rank{rank}.npz", gi=gi, gd=gd)
@@ -111,16 +121,17 @@ def _key_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_min_reduction_of_packed_keys_is_the_merge(tmp_path):
-    """Two MIN all-reduces over (d2 << 32 | row) keys give the single-database top-2: ties resolve to
-    the lowest row, a shard with a single row takes part, every rank ends with the same lists."""
+def test_key_exchange_is_the_merge(tmp_path):
+    """Packed (d2 << 32 | row) keys, all-to-all by query-row slice, two smallest per row, all-gather:
+    the single-database top-2 on every rank - ties resolve to the lowest row, a shard with a single
+    row takes part, the batch need not divide by the number of ranks."""
     world = 3
     mp.spawn(_key_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     sys.path.insert(0, str(ROOT / "tests"))
     from oracle import sod_oracle as O
     from scenes import sift_like
     rng = np.random.default_rng(79)
-    db = sift_like(rng, 3 * 200 + 1)
+    db = sift_like(rng, 601)
     q = sift_like(rng, 130)
     db[7] = db[420] = db[421] = q[0]
     db[600] = q[1]

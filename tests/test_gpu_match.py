@@ -175,45 +175,29 @@ def test_tile_ranges_and_carried_thresholds_stay_exact():
 
 
 def test_key_exchange_equals_list_merge():
-    """sod_top2_keys / sod_top2_runner_up / sod_top2_from_keys with torch.min standing in for the MIN
-    all-reduce: identical to sod_top2_merge over the gathered lists (ties, short shards, empty lists)."""
+    """sod_top2_keys / sod_top2_merge_keys / sod_top2_from_keys with tensor copies standing in for the
+    all-to-all and the all-gather: identical to sod_top2_merge over the gathered lists (ties, one-row
+    and empty shards, a batch that does not divide by the number of ranks)."""
     from sod_b200 import engine as E
     g = torch.Generator(device="cuda").manual_seed(5)
-    nq = 1000
+    nq = 1001
     q = torch.randint(0, 4, (nq, 128), dtype=torch.uint8, device="cuda", generator=g)      # many ties
     db = torch.randint(0, 4, (2500, 128), dtype=torch.uint8, device="cuda", generator=g)
     db[torch.randint(0, 2500, (200,), device="cuda", generator=g)] = q[:200]
     cuts = [0, 1, 1, 900, 2500]                                                             # 1-row and empty shards
-    lists = [E.Matcher(E.prepare_db(db[a:b].contiguous(), index_base=a)).top2(q) if b > a else
-             (torch.full((nq, 2), -1, dtype=torch.int32, device="cuda"),) * 2 for a, b in zip(cuts[:-1], cuts[1:])]
+    world = len(cuts) - 1
+    none = torch.full((nq, 2), -1, dtype=torch.int32, device="cuda")
+    lists = [E.Matcher(E.prepare_db(db[a:b].contiguous(), index_base=a)).top2(q) if b > a else (none, none)
+             for a, b in zip(cuts[:-1], cuts[1:])]
     want = E.merge_top2(torch.stack([i for i, _ in lists]), torch.stack([d for _, d in lists]))
-    # all "ranks" in sequence: keys, MIN, runner-up, MIN, unpack
-    nqd = nq
-    owns, bests = [], []
-    for i, d in lists:
-        own = torch.empty((2, nqd), dtype=torch.int64, device="cuda")
-        best = torch.empty(nqd, dtype=torch.int64, device="cuda")
-        E.check(E.lib.sod_top2_keys(i.data_ptr(), d.data_ptr(), nqd, own.data_ptr(), best.data_ptr(), None), "keys")
-        owns.append(own)
-        bests.append(best)
-    gbest = torch.stack(bests).min(0).values.contiguous()
-    seconds = []
-    for own in owns:
-        sec = torch.empty(nqd, dtype=torch.int64, device="cuda")
-        E.check(E.lib.sod_top2_runner_up(gbest.data_ptr(), own.data_ptr(), nqd, sec.data_ptr(), None), "runner_up")
-        seconds.append(sec)
-    gsec = torch.stack(seconds).min(0).values.contiguous()
-    oi = torch.empty((nqd, 2), dtype=torch.int32, device="cuda")
-    od = torch.empty((nqd, 2), dtype=torch.int32, device="cuda")
-    dist = torch.empty((nqd, 2), dtype=torch.float32, device="cuda")
-    ok = torch.empty(nqd, dtype=torch.uint8, device="cuda")
-    E.check(E.lib.sod_top2_from_keys(gbest.data_ptr(), gsec.data_ptr(), nqd, oi.data_ptr(), od.data_ptr(),
-                                     dist.data_ptr(), ok.data_ptr(), 0.75, None), "from_keys")
-    torch.cuda.synchronize()
-    for got, ref in zip((oi, od, dist, ok), want):
+    per = (nq + world - 1) // world
+    keys = [E.top2_keys(i, d, per * world) for i, d in lists]                  # every rank's send buffer
+    merged = torch.cat([E.merge_keys(torch.stack([k[r * per:(r + 1) * per] for k in keys]))
+                        for r in range(world)])                                # rank r merges slice r; gather
+    for got, ref in zip(E.top2_from_keys(merged, nq), want):
         assert torch.equal(got, ref)
-    # the engine wrapper on one rank (identity reduction) reproduces the single-shard merge
-    m = E.Matcher(E.prepare_db(db))
-    i1, d1 = m.top2(q)
-    for got, ref in zip(E.allreduce_merge_top2(i1, d1, lambda t: t), E.merge_top2(i1[None], d1[None])):
+    # the engine wrapper on one rank (both collectives are copies) reproduces the single-shard merge
+    i1, d1 = E.Matcher(E.prepare_db(db)).top2(q)
+    copy = lambda out, inp: out.copy_(inp)  # noqa: E731
+    for got, ref in zip(E.exchange_merge_top2(i1, d1, 1, copy, copy), E.merge_top2(i1[None], d1[None])):
         assert torch.equal(got, ref)
