@@ -50,6 +50,23 @@ def seed_query_slice(n_query: int, rank: int, world: int) -> tuple[int, int]:
     return min(lo, int(n_query)), min(hi, int(n_query))
 
 
+def local_hough_spaces(n_images: int, obj_lo: int, obj_hi: int) -> tuple[np.ndarray, int]:
+    """Hough spaces of one rank of a database-sharded run: only the rank's own objects [obj_lo, obj_hi)
+    can receive votes there, so they are numbered 0..n_local-1 -> (image_group int32 [n_images],
+    n_local).  Images of other ranks never occur in the rank's matches; they map to space 0."""
+    n_local = max(int(obj_hi) - int(obj_lo), 1)
+    grp = np.arange(n_images, dtype=np.int64) - int(obj_lo)
+    grp[(grp < 0) | (grp >= n_local)] = 0
+    return grp.astype(np.int32), n_local
+
+
+def global_space_ids(local_ids: np.ndarray, n_local: int, n_images: int, obj_lo: int) -> np.ndarray:
+    """Rank-local space ids (frame * n_local + local object) -> the single-GPU numbering
+    (frame * n_images + object)."""
+    local_ids = np.asarray(local_ids).astype(np.int64)
+    return ((local_ids // n_local) * n_images + obj_lo + local_ids % n_local).astype(np.int32)
+
+
 @dataclass
 class ModelDatabase:
     """Host-side description of the model database (what GenerateDatabaseInfo pickles, as arrays)."""
@@ -91,7 +108,7 @@ class DetectionPipeline:
         rows = np.bincount(image, minlength=n_images)
         if np.any(np.diff(image) < 0):
             raise ValueError("database rows must be grouped by model image")
-        _, _, self.row_lo, self.row_hi = shard_bounds(n_images, rows, rank, world)
+        self.obj_lo, self.obj_hi, self.row_lo, self.row_hi = shard_bounds(n_images, rows, rank, world)
         des = db.des[self.row_lo:self.row_hi]
         des_dev = (des if isinstance(des, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(des)))
         des_dev = des_dev.to(self.device).contiguous()
@@ -118,12 +135,18 @@ class DetectionPipeline:
         dev = self.device
         # query-side device buffers (filled by copy for host inputs, pointers stay stable)
         self.q_des = torch.empty((nq, 128), dtype=torch.float32 if self.float_path else torch.uint8, device=dev)
+        # One Hough space per (frame, object) - or per frame.  Results number them frame * spaces_per_frame +
+        # object; on the device a rank only carries the spaces of its own objects (the Hough stage scans
+        # all spaces of a batch, and a rank of a database-sharded run owns 1/G of the objects).
+        self.n_images = n_images
+        self.spaces_per_frame = n_images if per_object_spaces else 1
+        img_group, self._local_spaces = (local_hough_spaces(n_images, self.obj_lo, self.obj_hi)
+                                         if per_object_spaces else (None, 1))
         self.scene = E.SceneArrays(
             torch.zeros((nq, 2), dtype=torch.float32), torch.zeros(nq, dtype=torch.float32),
             torch.zeros(nq, dtype=torch.int32), db.xy, db.angle, db.octave, db.image, db.img_centroid,
             np.asarray(db.img_size, np.float64), frame_wh, q_frame=torch.zeros(nq, dtype=torch.int32),
-            img_group=np.arange(n_images, dtype=np.int32) if per_object_spaces else None,
-            groups_per_frame=n_images if per_object_spaces else 1, device=dev)
+            img_group=img_group, groups_per_frame=self._local_spaces, device=dev)
         self.voter = E.HoughVoter(self.scene, bins)
         self._aff: E.AffineResult | None = None
         # two sets of query-side buffers: set 0 is the one allocated above; set 1 appears on first use
@@ -272,7 +295,9 @@ class DetectionPipeline:
             votes=a.votes[:n_valid].cpu().numpy(), status=a.status[:n_valid].cpu().numpy())
         h = r["hough"]
         vb = a.valid_bin[:n_valid].long()
-        out["valid_group"] = h.bin_group[vb].cpu().numpy()
+        group = h.bin_group[vb].cpu().numpy()
+        out["valid_group"] = group if self._local_spaces == self.spaces_per_frame else \
+            global_space_ids(group, self._local_spaces, self.n_images, self.obj_lo)
         out["valid_code"] = h.bin_code[vb].cpu().numpy()
         out["valid_order"] = h.bin_order[vb].cpu().numpy()
         out["valid_mean"] = h.bin_mean[vb].cpu().numpy()
@@ -287,7 +312,7 @@ class DetectionPipeline:
         from .postprocess import post_process_arrays
         live = (out["status"] & 1).astype(bool)
         group, order, mean = out["valid_group"][live], out["valid_order"][live], out["valid_mean"][live]
-        frame = group // self.scene.groups_per_frame
+        frame = group // self.spaces_per_frame
         o = np.lexsort((order, group, frame))
         mean, frame = mean[o], frame[o].astype(np.int32)
         clusters, _, _, final = post_process_arrays(mean[:, 0], mean[:, 1], mean[:, 3], mean[:, 2], mean[:, 4],

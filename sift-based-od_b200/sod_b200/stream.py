@@ -169,7 +169,7 @@ class FrameStream:
         lo = sum(len(f) for f in feats[:slot])
         hi = lo + len(feats[slot])
         ok = out["ok"][lo:hi].astype(bool)
-        gpf = self.pipeline.scene.groups_per_frame
+        gpf = self.pipeline.spaces_per_frame
         mine = (out["valid_group"] // gpf) == slot
         return dict(match_q=np.nonzero(ok)[0].astype(np.int32), match_t=out["idx"][lo:hi, 0][ok],
                     n_descriptors=hi - lo, valid_group=out["valid_group"][mine] % gpf, valid_code=out["valid_code"][mine],

@@ -237,6 +237,29 @@ def test_seed_slices_and_sample():
     assert seed_sample_rows(10, 64).tolist() == list(range(10))
 
 
+def test_rank_local_hough_spaces_map_back_to_the_global_numbering():
+    """A rank of a database-sharded run numbers only its own objects' Hough spaces; results carry the
+    single-GPU ids frame * n_images + object."""
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    from sod_b200.pipeline import global_space_ids, local_hough_spaces, shard_bounds
+    n_images, frames = 11, 5
+    seen = []
+    for world in (1, 2, 3, 8):
+        for rank in range(world):
+            olo, ohi, _, _ = shard_bounds(n_images, 7, rank, world)
+            grp, n_local = local_hough_spaces(n_images, olo, ohi)
+            assert n_local == max(ohi - olo, 1) and grp.dtype == np.int32 and grp.min() >= 0 and grp.max() < n_local
+            own = np.arange(olo, ohi)
+            assert grp[own].tolist() == list(range(len(own)))           # own objects: dense, in order
+            f, o = np.meshgrid(np.arange(frames), own, indexing="ij")
+            local = (f * n_local + grp[o]).ravel()                      # what the Hough kernel computes
+            np.testing.assert_array_equal(global_space_ids(local, n_local, n_images, olo), (f * n_images + o).ravel())
+            if world == 1:
+                np.testing.assert_array_equal(global_space_ids(local, n_local, n_images, olo), local)
+            seen.append((world, rank))
+    assert len(seen) == 14
+
+
 def test_shard_bounds_are_object_aligned_and_cover():
     sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
     from sod_b200.pipeline import shard_bounds

@@ -26,6 +26,7 @@ class _EchoPipeline:
 
     def __init__(self, max_queries, n_frames):
         self.max_queries, self.scene = max_queries, _Scene(n_frames)
+        self.spaces_per_frame = 1
         self.calls = []
 
     def load_queries(self, des, xy, angle, octave, frame, slot=0, overlap=False):
