@@ -11,23 +11,24 @@ import math
 from sod_b200 import postprocess as _pp
 
 
-def dfs(i, seen, graph, out, items):
-    """Pre-order depth-first walk from i appending items[...] to out (reference :4-11), iterative."""
+def dfs(i, set, dict, pose_set, valid_bins):  # noqa: A002 - the reference's parameter names (:4)
+    """Pre-order depth-first walk from i appending valid_bins[...] to pose_set (reference :4-11), iterative."""
+    seen, graph = set, dict
     if i in seen:
-        return out
+        return pose_set
     seen.add(i)
-    out.append(items[i])
+    pose_set.append(valid_bins[i])
     stack = [iter(graph[i])]
     while stack:
         for nb in stack[-1]:
             if nb not in seen:
                 seen.add(nb)
-                out.append(items[nb])
+                pose_set.append(valid_bins[nb])
                 stack.append(iter(graph[nb]))
                 break
         else:
             stack.pop()
-    return out
+    return pose_set
 
 
 def group_position(valid_bins):
