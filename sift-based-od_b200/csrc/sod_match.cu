@@ -163,7 +163,11 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
   }
 }
 
-template <bool kShare>  // kShare: query rows are swept by several units that share their thresholds
+// kShare: query rows are swept by several units that share their thresholds through a.row_thr.
+// kSeeded (experimental, -DSOD_THR_INIT_ONLY): a.row_thr is only read when a unit starts and updated
+// once when it ends - for single-segment sweeps with caller-held thresholds, which have nobody to
+// share with inside the launch and should not pay the per-tile load of the sharing code.
+template <bool kShare, bool kSeeded = false>
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_db, const MatchArgs a) {
@@ -314,9 +318,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // best with atomicMin, everyone prunes with the minimum.  Any unit's 2nd best is an upper
       // bound of the row's final 2nd best, so this stays exact; without it every segment pays the
       // ~2 ln(n) threshold-establishing updates again.
-      int* const gthr = kShare ? a.row_thr + (qb * kBlockQ + h * kTileM + quad * 32 + lane) : nullptr;
+      int* const gthr = (kShare || kSeeded) ? a.row_thr + (qb * kBlockQ + h * kTileM + quad * 32 + lane) : nullptr;
       int published = kNoKey;
-      int thr = kShare ? min(kNoKey, __ldcg(gthr)) : kNoKey;
+      int thr = (kShare || kSeeded) ? min(kNoKey, __ldcg(gthr)) : kNoKey;
       for (int t = t0; t < t1; ++t, ++step) {
         if ((step & 1u) != par) continue;
         const uint32_t acc = step & 1u, bg = step % kBarGroups, bgph = (step / kBarGroups) & 1u;
@@ -349,6 +353,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
           thr = min(thr, g_next);
         }
       }
+      if (kSeeded && best.d2 < kNoKey) atomicMin(gthr, best.d2);
       if (row < a.nq) {
         const int qn = a.qn[row];
         const int64_t o = ((static_cast<int64_t>(seg) * kParity + par) * a.nq + row) * 2;
@@ -802,6 +807,9 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
 
   // The attribute is per device (a process may drive several), so it is set at every launch: ~1 us.
   auto* kernel = a.row_thr ? match_top2_kernel<true> : match_top2_kernel<false>;
+#ifdef SOD_THR_INIT_ONLY
+  if (row_thr && p.n_seg == 1) kernel = match_top2_kernel<false, true>;
+#endif
   SOD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
   SOD_CHECK_LAUNCH("match_top2_kernel");

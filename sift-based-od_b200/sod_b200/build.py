@@ -80,5 +80,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Kernel experiments: the same sources with extra -D flags -> libsod_b200.<name>.so next to the
+    shipped library (select it with SOD_B200_LIB; never loaded by default)."""
+    nvcc = _nvcc()
+    out = PKG_DIR / f"libsod_b200.{name}.so"
+    cmd = [nvcc, *NVCC_FLAGS, *defines, *map(str, _sources()), "-o", str(out), *LINK_FLAGS]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for variant {name}:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:    # python -m sod_b200.build --variant initonly -DSOD_THR_INIT_ONLY
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))
