@@ -63,6 +63,30 @@ def test_argument_checks_of_the_newer_entry_points_without_gpu():
     assert lib.sod_pose_adjacency(None, None, None, None, None, 0, None, None, None) == 0
 
 
+def test_key_exchange_entry_points_check_their_arguments_without_gpu():
+    from sod_b200 import _capi
+    lib = _capi.lib
+    assert lib.sod_top2_keys(None, None, 5, 4, None, None) == -1 and b"n_rows" in lib.sod_last_error()
+    assert lib.sod_top2_keys(None, None, 0, 0, None, None) == 0                       # nothing to do
+    assert lib.sod_top2_keys(None, None, 0, 8, None, None) == -1 and b"null" in lib.sod_last_error()
+    assert lib.sod_top2_keys(None, None, 0, 8, 24, None) == -1 and b"aligned" in lib.sod_last_error()
+    assert lib.sod_top2_merge_keys(None, -1, 4, None, None) == -1
+    assert lib.sod_top2_merge_keys(None, 2, 4, 16, None) == -1 and b"null" in lib.sod_last_error()
+    assert lib.sod_top2_merge_keys(None, 2, 0, None, None) == 0
+    assert lib.sod_top2_from_keys(None, 4, None, None, None, None, 0.75, None) == -1
+    assert lib.sod_row_thr_ints(0) == 0 and lib.sod_row_thr_ints(1) == 256 and lib.sod_row_thr_ints(257) == 512
+
+
+def test_ctypes_prototypes_have_the_arity_of_the_header():
+    """Every prototype bound in _capi.py takes as many arguments as include/sod.h declares."""
+    from sod_b200 import _capi
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "sod.h").read_text(), flags=re.S)
+    for name, params in re.findall(r"\b(sod_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_capi._PROTOS[name][1]) == n, name
+
+
 def test_product_does_not_import_the_oracle():
     pkg = ROOT / "sift-based-od_b200"
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
