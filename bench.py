@@ -115,6 +115,15 @@ def make_workload(args, device):
                 frame_wh=np.tile(np.array([[W, H]], np.int32), (frames, 1)), n_true=len(src_q))
 
 
+def make_database(wl):
+    """The workload's model database for DetectionPipeline: every model image is its own object, so the
+    Hough spaces are per (frame, object) and the database shards at object boundaries."""
+    from sod_b200.pipeline import ModelDatabase
+    return ModelDatabase(wl["db_des"], wl["m_xy"], wl["m_angle"], wl["m_octave"], wl["m_image"],
+                         wl["img_centroid"], wl["img_size"],
+                         object_of_image=np.arange(len(wl["img_centroid"]), dtype=np.int32))
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -283,7 +292,7 @@ def measure_int8_cublas_tops(device):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from sod_b200.pipeline import DetectionPipeline, ModelDatabase
+    from sod_b200.pipeline import DetectionPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -299,8 +308,7 @@ def run_ours(args):
 
     wl = make_workload(args, device)
     nq, ndb = args.frames * args.per_frame, args.objects * args.kp_per_object
-    db = ModelDatabase(wl["db_des"], wl["m_xy"], wl["m_angle"], wl["m_octave"], wl["m_image"],
-                       wl["img_centroid"], wl["img_size"])
+    db = make_database(wl)
     nq_total = nq
     if args.shard == "frames" and world > 1:
         # database replicated, frames split: rank r owns frames [r*F/N, (r+1)*F/N); no collective

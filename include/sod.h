@@ -273,6 +273,8 @@ typedef struct {
                            bit1 near-singular normal matrix, bits 8.. number of passes */
   uint8_t* member_keep; /* [cap_votes] aligned with sod_hough_out.members: 1 = still in its bin */
   int64_t cap_valid;
+  int64_t cap_votes;    /* elements of member_keep: a bin whose members end past it is not verified and
+                           sets the overflow counter (the array was sized for another Hough result) */
 } sod_affine_out;
 
 /* K5.  Main.get_valid_bins + Main.apply_affine_parameters (main.py:121-157) with AffineParameters

@@ -125,6 +125,12 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
     const int cnt = a.bin_count[rec];
     if (cnt > kSmallAffine) continue;
     const int off = a.bin_offset[rec];
+    if (static_cast<int64_t>(off) + cnt > a.out.cap_votes) {  // member_keep was sized for another Hough result
+      a.out.counters[1] = 1;
+      a.out.votes[v] = 0;
+      a.out.status[v] = 0;
+      continue;
+    }
     const int frame = a.bin_group[rec] / a.sc.groups_per_frame;
     const int isigma = a.bin_code[rec] % a.bins;
     const double x_ref = a.factor_x > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame] * isigma), a.factor_x) : inf;
@@ -191,6 +197,14 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
     const int rec = a.out.valid_bin[v];
     const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
     if (cnt <= kSmallAffine) continue;  // handled by affine_verify_small_kernel
+    if (static_cast<int64_t>(off) + cnt > a.out.cap_votes) {
+      if (lane == 0) {
+        a.out.counters[1] = 1;
+        a.out.votes[v] = 0;
+        a.out.status[v] = 0;
+      }
+      continue;
+    }
     const int frame = a.bin_group[rec] / a.sc.groups_per_frame;
     const int isigma = a.bin_code[rec] % a.bins;
     // remove_outliers thresholds use pose[3], the sigma BIN INDEX (AffineParameters.py:120-121)
@@ -288,8 +302,8 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
                                  int32_t max_passes, const sod_affine_out* out, sod_stream_t stream) {
   SOD_CHECK_ARG(scene && hough && out, "null scene/hough/out");
   SOD_CHECK_ARG(out->counters && out->valid_bin && out->params && out->votes && out->status &&
-                    out->member_keep && out->cap_valid > 0,
-                "null output array");
+                    out->member_keep && out->cap_valid > 0 && out->cap_votes > 0,
+                "null output array or zero capacity");
   SOD_CHECK_ARG(bins >= 1, "bins out of range");
   SOD_CHECK_ARG(match_q && match_t && hough->counters && hough->bin_group && hough->bin_code &&
                     hough->bin_count && hough->bin_offset && hough->members,

@@ -54,7 +54,7 @@ class HoughOut(C.Structure):
 
 class AffineOut(C.Structure):
     _fields_ = [("counters", _p), ("valid_bin", _p), ("params", _p), ("votes", _p), ("status", _p),
-                ("member_keep", _p), ("cap_valid", _i64)]
+                ("member_keep", _p), ("cap_valid", _i64), ("cap_votes", _i64)]
 
 
 SIGMA_LUT_MIN = -24

@@ -448,6 +448,13 @@ class HoughVoter:
         self._ws = None
         self._res: HoughResult | None = None
 
+    def reserve(self, m_cap: int) -> HoughResult:
+        """Size the outputs for up to m_cap matches now, so that later calls of any smaller size reuse
+        the same buffers (callers that keep an AffineResult across calls rely on this)."""
+        if self._res is None or self._res.m_cap < int(m_cap):
+            self._res = HoughResult(int(m_cap), self.scene.n_groups, self.dims, self.scene.device)
+        return self._res
+
     def vote(self, match_q: torch.Tensor, match_t: torch.Tensor, n_dev: torch.Tensor | None = None,
              detail_min_count: int = 1) -> HoughResult:
         """detail_min_count: bins with fewer votes get a record and a count but no sorted members,
@@ -459,9 +466,7 @@ class HoughVoter:
         need = int(lib.sod_hough_workspace_bytes(m, sc.n_groups))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=sc.device)
-        if self._res is None or self._res.m_cap < m:
-            self._res = HoughResult(m, sc.n_groups, self.dims, sc.device)
-        res = self._res
+        res = self.reserve(m)
         s, o = sc.struct(), res.struct()
         check(lib.sod_hough_vote_dims(C.byref(s), _ptr(match_q), _ptr(match_t), m, _ptr(n_dev), *self.dims,
                                       _ptr(self.lut), int(detail_min_count), C.byref(o), _ptr(self._ws),
@@ -472,7 +477,11 @@ class HoughVoter:
 
 class AffineResult:
     def __init__(self, hough: HoughResult, vote_threshold: int, device):
-        self.cap_valid = max(1, min(hough.cap_bins, hough.cap_votes // max(vote_threshold, 1)))
+        # a bin enters with >= vote_threshold votes; with no threshold every record may enter (empty
+        # bins of a caller-built list included), so the bound by votes does not apply
+        self.cap_valid = max(1, hough.cap_bins if vote_threshold <= 0 else
+                             min(hough.cap_bins, hough.cap_votes // vote_threshold))
+        self.cap_votes = hough.cap_votes
         self.counters = torch.zeros(2, dtype=torch.int32, device=device)
         self.valid_bin = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
         self.params = torch.empty((self.cap_valid, 6), dtype=torch.float64, device=device)
@@ -482,7 +491,7 @@ class AffineResult:
 
     def struct(self) -> AffineOut:
         return AffineOut(_ptr(self.counters), _ptr(self.valid_bin), _ptr(self.params), _ptr(self.votes),
-                         _ptr(self.status), _ptr(self.member_keep), self.cap_valid)
+                         _ptr(self.status), _ptr(self.member_keep), self.cap_valid, self.cap_votes)
 
     def host(self, n_votes: int) -> dict:
         c = self.counters.cpu().numpy()
@@ -501,6 +510,9 @@ def affine_verify(scene: SceneArrays, match_q: torch.Tensor, match_t: torch.Tens
                   result: AffineResult | None = None, factor_y: float | None = None,
                   max_passes: int = 0) -> AffineResult:
     res = result or AffineResult(hough, vote_threshold, scene.device)
+    if res.cap_votes < hough.cap_votes:
+        raise ValueError(f"AffineResult sized for {res.cap_votes} votes cannot take a Hough result of "
+                         f"{hough.cap_votes}: build it from this HoughResult (or reserve the voter first)")
     s, h, o = scene.struct(), hough.struct(), res.struct()
     check(lib.sod_affine_verify(C.byref(s), _ptr(match_q), _ptr(match_t), C.byref(h), hough.bins,
                                 int(vote_threshold), int(affine_threshold), float(factor),

@@ -50,21 +50,24 @@ def seed_query_slice(n_query: int, rank: int, world: int) -> tuple[int, int]:
     return min(lo, int(n_query)), min(hi, int(n_query))
 
 
-def local_hough_spaces(n_images: int, obj_lo: int, obj_hi: int) -> tuple[np.ndarray, int]:
+def local_hough_spaces(object_of_image, obj_lo: int, obj_hi: int) -> tuple[np.ndarray, int]:
     """Hough spaces of one rank of a database-sharded run: only the rank's own objects [obj_lo, obj_hi)
     can receive votes there, so they are numbered 0..n_local-1 -> (image_group int32 [n_images],
-    n_local).  Images of other ranks never occur in the rank's matches; they map to space 0."""
+    n_local).  object_of_image: the object of every model image (an int n means n images, each its own
+    object).  Images of other ranks never occur in the rank's matches; they map to space 0."""
     n_local = max(int(obj_hi) - int(obj_lo), 1)
-    grp = np.arange(n_images, dtype=np.int64) - int(obj_lo)
+    obj = np.arange(object_of_image, dtype=np.int64) if np.isscalar(object_of_image) else \
+        np.asarray(object_of_image).astype(np.int64)
+    grp = obj - int(obj_lo)
     grp[(grp < 0) | (grp >= n_local)] = 0
     return grp.astype(np.int32), n_local
 
 
-def global_space_ids(local_ids: np.ndarray, n_local: int, n_images: int, obj_lo: int) -> np.ndarray:
+def global_space_ids(local_ids: np.ndarray, n_local: int, n_objects: int, obj_lo: int) -> np.ndarray:
     """Rank-local space ids (frame * n_local + local object) -> the single-GPU numbering
-    (frame * n_images + object)."""
+    (frame * n_objects + object)."""
     local_ids = np.asarray(local_ids).astype(np.int64)
-    return ((local_ids // n_local) * n_images + obj_lo + local_ids % n_local).astype(np.int32)
+    return ((local_ids // n_local) * n_objects + obj_lo + local_ids % n_local).astype(np.int32)
 
 
 @dataclass
@@ -77,19 +80,30 @@ class ModelDatabase:
     image: np.ndarray                # i32 [N] model image (= object) of each row, non-decreasing
     img_centroid: np.ndarray         # f64 [n_images,2]
     img_size: np.ndarray             # [n_images,2] (w,h)
+    object_of_image: np.ndarray | None = None   # i32 [n_images] object of every model image, non-decreasing;
+                                                # None = the reference's database: training views of ONE object
 
 
 class DetectionPipeline:
     def __init__(self, db: ModelDatabase, max_queries: int, frame_wh: np.ndarray, rank: int = 0,
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
-                 affine_threshold: int = 4, per_object_spaces: bool = True, device: str | torch.device = "cuda",
-                 shard: str = "db", seed_rows: int = 0, exchange: str = "scatter"):
-        """shard="db": database rows split over the ranks, one exchange of the shard-local top-2.
-        shard="frames": database replicated on every rank, the caller gives each rank its own frames
-        (no collective at all); the pipeline then behaves exactly like a single-GPU one.
+                 affine_threshold: int = 4, per_object_spaces: bool | None = None,
+                 device: str | torch.device = "cuda", shard: str = "db", seed_rows: int = 0,
+                 exchange: str = "scatter"):
+        """Hough spaces.  The reference votes ALL model images into one dict (main.py:30,113-119: the
+        database is several training views of one object), and that is the default here: one space
+        per frame.  A multi-object database names the object of every model image in
+        db.object_of_image; every (frame, object) pair then gets its own space (the key is
+        extended to (object, pose); with one object it is the reference).  per_object_spaces=None
+        follows the database (object map present -> per object); True without a map treats every image
+        as its own object; False forces the single space.
+        shard="db": database rows split over the ranks at object boundaries, one exchange of the
+        shard-local top-2; needs per-object spaces when world > 1, because the votes of
+        one space must meet on one rank.  shard="frames": database replicated on every rank, the caller
+        gives each rank its own frames (no collective at all); the pipeline then behaves exactly like a
+        single-GPU one.
         seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
-        seeds the pruning thresholds (see detect_device).  Off by default: measured on B200 it saves
-        less than its own sweep and the sharing kernel instance cost.
+        seeds the pruning thresholds (see detect_device); 0 = off.
         exchange (shard="db"): "scatter" = all-to-all of packed keys, slice merge, all-gather of the merged
         slices; "gather" = all-gather of every rank's lists + sod_top2_merge on every rank."""
         if shard not in ("db", "frames"):
@@ -105,10 +119,25 @@ class DetectionPipeline:
         self.bins, self.vote_threshold, self.affine_threshold = bins, vote_threshold, affine_threshold
         n_images = int(db.img_centroid.shape[0])
         image = np.asarray(db.image)
-        rows = np.bincount(image, minlength=n_images)
         if np.any(np.diff(image) < 0):
             raise ValueError("database rows must be grouped by model image")
-        self.obj_lo, self.obj_hi, self.row_lo, self.row_hi = shard_bounds(n_images, rows, rank, world)
+        if per_object_spaces is None:
+            per_object_spaces = db.object_of_image is not None
+        if per_object_spaces:
+            obj_of_img = (np.arange(n_images, dtype=np.int32) if db.object_of_image is None
+                          else np.asarray(db.object_of_image).astype(np.int32))
+            if obj_of_img.shape != (n_images,) or np.any(np.diff(obj_of_img) < 0) or (n_images and obj_of_img[0] < 0):
+                raise ValueError("object_of_image must give a non-decreasing object id >= 0 for every model image")
+        else:
+            obj_of_img = np.zeros(n_images, np.int32)
+        if world > 1 and not per_object_spaces:
+            # one Hough space for all model images: its votes would be spread over the ranks and never
+            # meet in a bin, so counts, thresholds and running means would differ from one GPU
+            raise ValueError("shard='db' over several ranks needs per-object Hough spaces (give the database an "
+                             "object_of_image map); use shard='frames' for the reference's single space")
+        n_objects = int(obj_of_img.max()) + 1 if n_images else 1
+        rows = np.bincount(obj_of_img[image], minlength=n_objects) if len(image) else np.zeros(n_objects, np.int64)
+        self.obj_lo, self.obj_hi, self.row_lo, self.row_hi = shard_bounds(n_objects, rows, rank, world)
         des = db.des[self.row_lo:self.row_hi]
         des_dev = (des if isinstance(des, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(des)))
         des_dev = des_dev.to(self.device).contiguous()
@@ -139,8 +168,9 @@ class DetectionPipeline:
         # object; on the device a rank only carries the spaces of its own objects (the Hough stage scans
         # all spaces of a batch, and a rank of a database-sharded run owns 1/G of the objects).
         self.n_images = n_images
-        self.spaces_per_frame = n_images if per_object_spaces else 1
-        img_group, self._local_spaces = (local_hough_spaces(n_images, self.obj_lo, self.obj_hi)
+        self.n_objects = n_objects
+        self.spaces_per_frame = n_objects if per_object_spaces else 1
+        img_group, self._local_spaces = (local_hough_spaces(obj_of_img, self.obj_lo, self.obj_hi)
                                          if per_object_spaces else (None, 1))
         self.scene = E.SceneArrays(
             torch.zeros((nq, 2), dtype=torch.float32), torch.zeros(nq, dtype=torch.float32),
@@ -148,7 +178,10 @@ class DetectionPipeline:
             np.asarray(db.img_size, np.float64), frame_wh, q_frame=torch.zeros(nq, dtype=torch.int32),
             img_group=img_group, groups_per_frame=self._local_spaces, device=dev)
         self.voter = E.HoughVoter(self.scene, bins)
-        self._aff: E.AffineResult | None = None
+        # Outputs of the Hough and affine stages are sized ONCE for max_queries: a later, larger batch
+        # must never meet buffers that were sized for an earlier, smaller one.
+        self._hough = self.voter.reserve(nq)
+        self._aff = E.AffineResult(self._hough, self.vote_threshold, self.device)
         # two sets of query-side buffers: set 0 is the one allocated above; set 1 appears on first use
         self._qsets = [dict(des=self.q_des, xy=self.scene.q_xy, angle=self.scene.q_angle,
                             octave=self.scene.q_octave, frame=self.scene.q_frame), None]
@@ -248,8 +281,6 @@ class DetectionPipeline:
         lo, hi = (self.row_lo, self.row_hi) if self.world > 1 else (0, 2 ** 31 - 1)
         mq, mt, n_dev = E.compact_matches(idx, ok, lo, hi)
         hough = self.voter.vote(mq, mt, n_dev, detail_min_count=self.vote_threshold)
-        if self._aff is None:
-            self._aff = E.AffineResult(hough, self.vote_threshold, self.device)
         aff = E.affine_verify(self.scene, mq, mt, hough, self.vote_threshold, self.affine_threshold,
                               result=self._aff)
         self._consumed[slot] = torch.cuda.Event()
@@ -297,7 +328,7 @@ class DetectionPipeline:
         vb = a.valid_bin[:n_valid].long()
         group = h.bin_group[vb].cpu().numpy()
         out["valid_group"] = group if self._local_spaces == self.spaces_per_frame else \
-            global_space_ids(group, self._local_spaces, self.n_images, self.obj_lo)
+            global_space_ids(group, self._local_spaces, self.n_objects, self.obj_lo)
         out["valid_code"] = h.bin_code[vb].cpu().numpy()
         out["valid_order"] = h.bin_order[vb].cpu().numpy()
         out["valid_mean"] = h.bin_mean[vb].cpu().numpy()

@@ -26,8 +26,7 @@ def main():
                               inlier_frac=0.2, false_frac=0.02))()
     wl = bench.make_workload(args, dev)
     nq = args.frames * args.per_frame
-    db = ModelDatabase(wl["db_des"], wl["m_xy"], wl["m_angle"], wl["m_octave"], wl["m_image"],
-                       wl["img_centroid"], wl["img_size"])
+    db = bench.make_database(wl)
     q = (wl["q_des"], wl["q_xy"], wl["q_angle"], wl["q_octave"], wl["q_frame"])
     sharded = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev).detect(*q)
     # the same with threshold seeding forced on (it is automatic only for large databases): a replicated

@@ -272,3 +272,35 @@ def test_shard_bounds_are_object_aligned_and_cover():
         assert prev == 1_000_000
     rows = np.array([3, 0, 5, 2])
     assert [shard_bounds(4, rows, r, 2)[2:] for r in range(2)] == [(0, 3), (3, 10)]
+
+
+def test_single_hough_space_cannot_be_database_sharded():
+    """The reference's one Hough space for all model images cannot be split by database rows: votes of
+    one space would land on different ranks.  The constructor refuses before touching the device."""
+    import pytest
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    from sod_b200.pipeline import DetectionPipeline, ModelDatabase
+    n = 40
+    db = ModelDatabase(np.zeros((n, 128), np.uint8), np.zeros((n, 2), np.float32), np.zeros(n, np.float32),
+                       np.zeros(n, np.int32), np.repeat(np.arange(4, dtype=np.int32), 10), np.zeros((4, 2)),
+                       np.ones((4, 2), np.int32))
+    with pytest.raises(ValueError, match="per-object"):
+        DetectionPipeline(db, 16, np.array([[640, 480]], np.int32), rank=0, world=2)
+    with pytest.raises(ValueError, match="per-object"):
+        DetectionPipeline(db, 16, np.array([[640, 480]], np.int32), rank=1, world=2, per_object_spaces=False)
+    db.object_of_image = np.array([0, 0, 2, 1], np.int32)
+    with pytest.raises(ValueError, match="non-decreasing"):
+        DetectionPipeline(db, 16, np.array([[640, 480]], np.int32), rank=0, world=2)
+
+
+def test_shards_split_at_object_boundaries_when_objects_have_several_images():
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    from sod_b200.pipeline import global_space_ids, local_hough_spaces, shard_bounds
+    obj_of_img = np.array([0, 0, 0, 1, 2, 2], np.int32)          # 3 objects, 6 training images
+    image = np.repeat(np.arange(6), [5, 3, 2, 7, 4, 4])
+    rows = np.bincount(obj_of_img[image], minlength=3)
+    assert rows.tolist() == [10, 7, 8]
+    assert [shard_bounds(3, rows, r, 2) for r in range(2)] == [(0, 1, 0, 10), (1, 3, 10, 25)]
+    grp, n_local = local_hough_spaces(obj_of_img, 1, 3)
+    assert n_local == 2 and grp.tolist() == [0, 0, 0, 0, 1, 1]
+    np.testing.assert_array_equal(global_space_ids(np.array([0, 1, 2, 3]), 2, 3, 1), [1, 2, 4, 5])

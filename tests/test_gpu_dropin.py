@@ -154,3 +154,26 @@ def test_main_takes_the_bf16_path_for_non_integer_descriptors():
     m.run_matcher()
     assert [t[1].class_id for t in m.matching_keypoints] == z["match_q"].tolist()
     assert [t[0].class_id for t in m.matching_keypoints] == z["match_t"].tolist()
+
+
+def test_affine_on_a_bin_list_with_empty_and_tiny_bins():
+    """apply_affine_parameters-style use of the drop-in on a caller-built PoseBin list that contains an
+    empty bin and single-pair bins (more bins than pairs): the reference simply iterates; the capacity
+    of the device output must not be bounded by the number of pairs."""
+    from sod_b200 import dropin
+    from PoseBin import PoseBin
+    kp = lambda x, y: cv2.KeyPoint(float(x), float(y), 1.0, 0.0, 0.0, 0, 0)  # noqa: E731
+    rng = np.random.default_rng(5)
+    full = PoseBin((3, 4, 5, 2), (100, 100), 0, [], (0, 0, 0, 0))
+    for _ in range(9):
+        x, y = rng.uniform(0, 500, 2)
+        full.keypoint_pairs.append((kp(x, y), kp(2 * x + 10, 2 * y - 5)))
+    bins = [PoseBin((0, 0, 0, 2), (100, 100), 0, [], (0, 0, 0, 0)) for _ in range(12)]     # empty bins
+    one = PoseBin((1, 1, 1, 2), (100, 100), 0, [(kp(1, 2), kp(3, 4))], (0, 0, 0, 0))
+    out = dropin.affine_run(bins[:6] + [full, one] + bins[6:], (1000, 800), 128.0, 128.0, 4, 0)
+    assert len(out) == 14
+    params, keep, votes, live = out[6]
+    assert live and votes == 9 and keep.all()
+    np.testing.assert_allclose(params, [2, 0, 0, 2, 10, -5], rtol=1e-6, atol=1e-5)
+    assert out[0][0] is None and out[0][2] == 0 and not out[0][3]
+    assert out[7][2] <= 1 and not out[7][3]

@@ -18,8 +18,7 @@ def main():
                               inlier_frac=0.10, false_frac=0.01))()
     dev = torch.device("cuda")
     wl = bench.make_workload(args, dev)
-    db = ModelDatabase(wl["db_des"], wl["m_xy"], wl["m_angle"], wl["m_octave"], wl["m_image"],
-                       wl["img_centroid"], wl["img_size"])
+    db = bench.make_database(wl)
     nq = args.frames * args.per_frame
     host = tuple(torch.as_tensor(wl[k]).cpu().pin_memory() for k in ("q_des", "q_xy", "q_angle", "q_octave", "q_frame"))
     pipe = DetectionPipeline(db, nq, wl["frame_wh"], device=dev)
