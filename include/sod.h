@@ -41,6 +41,21 @@ const char* sod_last_error(void);
 /* Number of SMs of the current device (grid sizing; 148 on B200). Negative on error. */
 int sod_device_sm_count(void);
 
+/* Measurement hook (bench.py's roofline figures; nothing in the reference): while enabled on the
+ * calling thread, every entry point brackets the launches of the stages below with CUDA events on the
+ * caller's stream (up to 128 calls per stage between reads; no synchronisation, two event records per
+ * stage).  sod_timing_read waits for the recorded events of one stage, writes their durations in
+ * milliseconds to ms_host (HOST pointer, oldest first, at most cap), forgets them and returns how many
+ * it wrote (negative = error). */
+#define SOD_STAGE_MATCH 0        /* match_top2_kernel alone (without the list merge that follows it) */
+#define SOD_STAGE_HOUGH_PREP 1   /* pose + counting sort by Hough space */
+#define SOD_STAGE_HOUGH_VOTE 2   /* hough_vote_kernel alone */
+#define SOD_STAGE_HOUGH_FINISH 3 /* member order, running means, insertion keys */
+#define SOD_STAGE_AFFINE 4       /* select + verify kernels */
+#define SOD_STAGE_COUNT 5
+int sod_timing_enable(int32_t on);
+int32_t sod_timing_read(int32_t stage, float* ms_host, int32_t cap);
+
 /* Number of int32 elements of the prepared per-row constants `cq` for a database of n_rows:
  * ceil(n_rows / SOD_TILE_ROWS) * SOD_CQ_TILE_INTS. */
 int64_t sod_cq_ints(int64_t n_rows);

@@ -319,6 +319,7 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
   a.bin_offset = hough->bin_offset; a.members = hough->members; a.cap_bins = hough->cap_bins;
   a.bins = bins; a.vote_threshold = vote_threshold; a.affine_threshold = affine_threshold;
   a.factor_x = factor_x; a.factor_y = factor_y; a.max_passes = max_passes; a.out = *out;
+  StageScope timed(SOD_STAGE_AFFINE, st);
   affine_select_kernel<<<sms * 4, 256, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_select_kernel");
   affine_verify_small_kernel<<<sms * 8, 128, 0, st>>>(a);

@@ -12,6 +12,17 @@ namespace sod {
 void set_error(const char* fmt, ...);
 int device_sm_count();
 
+// Measurement hook behind sod_timing_enable / sod_timing_read: when enabled on the calling thread, the
+// entry points bracket the named stage's launches with CUDA events on the caller's stream.
+void stage_begin(int stage, cudaStream_t st);
+void stage_end(int stage, cudaStream_t st);
+struct StageScope {
+  int stage;
+  cudaStream_t st;
+  StageScope(int s, cudaStream_t stream) : stage(s), st(stream) { stage_begin(stage, st); }
+  ~StageScope() { stage_end(stage, st); }
+};
+
 #define SOD_CHECK_ARG(cond, ...)        \
   do {                                  \
     if (!(cond)) {                      \

@@ -707,6 +707,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   const int threads = 256;
   int64_t blocks = (n_matches + threads - 1) / threads;
   if (blocks > static_cast<int64_t>(sms) * 16) blocks = static_cast<int64_t>(sms) * 16;
+  stage_begin(SOD_STAGE_HOUGH_PREP, st);
   hough_pose_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(pa);
   SOD_CHECK_LAUNCH("hough_pose_kernel");
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.group_count, n_groups, w.group_off, w.group_cursor, nullptr);
@@ -714,6 +715,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
       w.group_of, out->base_bin, n_matches_dev, n_matches, w.group_cursor, w.grouped, w.grouped_base);
   SOD_CHECK_LAUNCH("group_scatter_kernel");
+  stage_end(SOD_STAGE_HOUGH_PREP, st);
 
   VoteArgs va;
   va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.creator = w.creator;
@@ -728,7 +730,10 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   va.group_chunk = static_cast<int>(group_chunk);
   const int64_t n_chunks = (n_groups + group_chunk - 1) / group_chunk;
   const int64_t vgrid = n_chunks < sms ? n_chunks : sms;
-  hough_vote_kernel<<<static_cast<unsigned>(vgrid), kVoteThreads, hist_bytes, st>>>(va);
+  {
+    StageScope timed(SOD_STAGE_HOUGH_VOTE, st);
+    hough_vote_kernel<<<static_cast<unsigned>(vgrid), kVoteThreads, hist_bytes, st>>>(va);
+  }
   SOD_CHECK_LAUNCH("hough_vote_kernel");
 
   FinishArgs fa;
@@ -739,10 +744,12 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   fa.bin_mean = out->bin_mean; fa.cap_bins = out->cap_bins; fa.bins = bins;
   fa.detail_min_count = detail_min_count; fa.big_list = w.big_list; fa.big_count = w.ticket + 1;
   fa.big_cap = w.big_cap;
+  stage_begin(SOD_STAGE_HOUGH_FINISH, st);
   hough_finish_kernel<<<sms * 8, 256, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_kernel");
   hough_finish_big_kernel<<<sms * 8, 256, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_big_kernel");
+  stage_end(SOD_STAGE_HOUGH_FINISH, st);
   return SOD_OK;
 }
 

@@ -164,9 +164,11 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
 }
 
 // kShare: query rows are swept by several units that share their thresholds through a.row_thr.
-// kSeeded (experimental, -DSOD_THR_INIT_ONLY): a.row_thr is only read when a unit starts and updated
-// once when it ends - for single-segment sweeps with caller-held thresholds, which have nobody to
-// share with inside the launch and should not pay the per-tile load of the sharing code.
+// kSeeded: a.row_thr is only read when a unit starts and updated once when it ends - for
+// single-segment sweeps with caller-held thresholds (the seeded shard sweeps of a database-sharded
+// run), which have nobody to share with inside the launch and must not pay the per-tile load and
+// atomicMin of the sharing code (B200, 1.28 M queries x 125k-row shard: 15.27 ms against 16.21 ms
+// with the sharing instance and 16.44 ms unseeded; profiles/r02_threshold_seeding.txt).
 template <bool kShare, bool kSeeded = false>
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -807,11 +809,12 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
 
   // The attribute is per device (a process may drive several), so it is set at every launch: ~1 us.
   auto* kernel = a.row_thr ? match_top2_kernel<true> : match_top2_kernel<false>;
-#ifdef SOD_THR_INIT_ONLY
   if (row_thr && p.n_seg == 1) kernel = match_top2_kernel<false, true>;
-#endif
   SOD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
+  {
+    StageScope timed(SOD_STAGE_MATCH, st);
+    kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
+  }
   SOD_CHECK_LAUNCH("match_top2_kernel");
   top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(a.part_idx, a.part_d2, p.n_seg * kParity, n_query,
                                                   out_idx, out_d2, nullptr, nullptr, 0.0);

@@ -57,6 +57,22 @@ class AffineOut(C.Structure):
                 ("member_keep", _p), ("cap_valid", _i64), ("cap_votes", _i64)]
 
 
+STAGES = {"match": 0, "hough_prep": 1, "hough_vote": 2, "hough_finish": 3, "affine": 4}
+
+
+def timing_enable(on: bool = True) -> None:
+    check(lib.sod_timing_enable(int(on)), "sod_timing_enable")
+
+
+def timing_read(stage: str) -> list[float]:
+    """Durations (ms) of the named stage's launches since the last read; waits for them."""
+    buf = (C.c_float * 128)()
+    n = int(lib.sod_timing_read(STAGES[stage], C.cast(buf, _p), 128))
+    if n < 0:
+        check(n, "sod_timing_read")
+    return [float(buf[i]) for i in range(n)]
+
+
 SIGMA_LUT_MIN = -24
 SIGMA_LUT_LEN = 49
 MAX_BINS = 15
@@ -65,6 +81,8 @@ _PROTOS = {
     "sod_version": (C.c_int, []),
     "sod_last_error": (C.c_char_p, []),
     "sod_device_sm_count": (C.c_int, []),
+    "sod_timing_enable": (C.c_int, [_i32]),
+    "sod_timing_read": (_i32, [_i32, _p, _i32]),
     "sod_cq_ints": (_i64, [_i64]),
     "sod_pack_u8_from_f32": (C.c_int, [_p, _i64, _p, _p, _p]),
     "sod_db_prepare_workspace_bytes": (C.c_size_t, [_i64]),

@@ -31,7 +31,9 @@ def shard_bounds(n_objects: int, rows_per_object: np.ndarray | int, rank: int, w
     return obj_lo, obj_hi, int(starts[obj_lo]), int(starts[obj_hi])
 
 
-SEED_ROWS = 16384          # a sensible size of the optional threshold-seeding sample of a sharded database
+SEED_ROWS = 16384          # size of the threshold-seeding sample of a sharded database
+SEED_MIN_DB_ROWS = 262144  # smaller databases are not seeded by default: the sweep is short anyway
+SEED_MIN_QUERIES = 65536   # smaller batches skip the seeding sweep: a launch and an all-reduce cost more
 QUERY_BLOCK = 256          # query rows per matcher unit: threshold slices must start on this boundary
 
 
@@ -88,8 +90,8 @@ class DetectionPipeline:
     def __init__(self, db: ModelDatabase, max_queries: int, frame_wh: np.ndarray, rank: int = 0,
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
                  affine_threshold: int = 4, per_object_spaces: bool | None = None,
-                 device: str | torch.device = "cuda", shard: str = "db", seed_rows: int = 0,
-                 exchange: str = "scatter"):
+                 device: str | torch.device = "cuda", shard: str = "db", seed_rows: int | None = None,
+                 exchange: str = "scatter", replicated_host: bool = True, result_rows: str = "all"):
         """Hough spaces.  The reference votes ALL model images into one dict (main.py:30,113-119: the
         database is several training views of one object), and that is the default here: one space
         per frame.  A multi-object database names the object of every model image in
@@ -103,14 +105,25 @@ class DetectionPipeline:
         gives each rank its own frames (no collective at all); the pipeline then behaves exactly like a
         single-GPU one.
         seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
-        seeds the pruning thresholds (see detect_device); 0 = off.
+        seeds the pruning thresholds (see detect_device); 0 = off; None = SEED_ROWS when the database has
+        at least SEED_MIN_DB_ROWS rows.  Batches below SEED_MIN_QUERIES rows skip the seeding sweep.
+        replicated_host (shard="db", several ranks): every rank is handed the same HOST batch, so each
+        uploads only its 1/G slice of the rows over its own PCIe link and one all-gather over NVLink
+        replicates it on the devices (load_queries); False = every rank uploads the whole batch.
+        result_rows (shard="db", several ranks): "all" = fetch() returns the match lists of every query
+        row on every rank; "own" = only the rows of the rank's slice (out["row_lo"] is the first), which
+        is all a caller that collects the ranks' answers needs.
         exchange (shard="db"): "scatter" = all-to-all of packed keys, slice merge, all-gather of the merged
         slices; "gather" = all-gather of every rank's lists + sod_top2_merge on every rank."""
         if shard not in ("db", "frames"):
             raise ValueError("shard must be 'db' or 'frames'")
         if exchange not in ("scatter", "gather"):
             raise ValueError("exchange must be 'scatter' or 'gather'")
+        if result_rows not in ("all", "own"):
+            raise ValueError("result_rows must be 'all' or 'own'")
         self.exchange = exchange
+        self.replicated_host, self.result_rows = bool(replicated_host), result_rows
+        self.seed_min_queries = SEED_MIN_QUERIES
         self.shard_mode = shard
         if shard == "frames":
             rank, world = 0, 1
@@ -154,13 +167,16 @@ class DetectionPipeline:
             # Database-sharded runs keep a small even sample of the WHOLE database on every rank; it only
             # seeds pruning thresholds (detect_device).  The choice depends on the whole database and on
             # the argument alone, so it is the same on every rank.
+            if seed_rows is None:
+                seed_rows = SEED_ROWS if len(image) >= SEED_MIN_DB_ROWS else 0
             if world > 1 and seed_rows > 0:
                 rows = seed_sample_rows(len(image), seed_rows)
                 sample = db.des[torch.from_numpy(rows)] if isinstance(db.des, torch.Tensor) else \
                     torch.from_numpy(np.ascontiguousarray(np.asarray(db.des)[rows]))
                 self.seed_matcher = E.Matcher(E.prepare_db(sample.to(self.device).contiguous(), index_base=0))
         self.max_queries = int(max_queries)
-        nq = self.max_queries
+        # capacity of the query-side buffers: whole slices of ceil(n / world) rows for every n <= max_queries
+        nq = self.max_queries + (world - 1 if world > 1 else 0)
         dev = self.device
         # query-side device buffers (filled by copy for host inputs, pointers stay stable)
         self.q_des = torch.empty((nq, 128), dtype=torch.float32 if self.float_path else torch.uint8, device=dev)
@@ -180,7 +196,7 @@ class DetectionPipeline:
         self.voter = E.HoughVoter(self.scene, bins)
         # Outputs of the Hough and affine stages are sized ONCE for max_queries: a later, larger batch
         # must never meet buffers that were sized for an earlier, smaller one.
-        self._hough = self.voter.reserve(nq)
+        self._hough = self.voter.reserve(self.max_queries)
         self._aff = E.AffineResult(self._hough, self.vote_threshold, self.device)
         # two sets of query-side buffers: set 0 is the one allocated above; set 1 appears on first use
         self._qsets = [dict(des=self.q_des, xy=self.scene.q_xy, angle=self.scene.q_angle,
@@ -189,9 +205,9 @@ class DetectionPipeline:
         self._loaded = [None, None]      # event: the set's host->device copies have landed
         self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
         if world > 1 and (self.float_path or self.exchange == "gather"):
-            self._gather_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
-            self._gather_d2 = torch.empty((world, nq, 2), dtype=torch.float32 if self.float_path else torch.int32,
-                                          device=dev)
+            self._gather_idx = torch.empty((world, self.max_queries, 2), dtype=torch.int32, device=dev)
+            self._gather_d2 = torch.empty((world, self.max_queries, 2),
+                                          dtype=torch.float32 if self.float_path else torch.int32, device=dev)
         # our kernels per detect_device call; the key exchange of a database-sharded run is
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
@@ -204,15 +220,27 @@ class DetectionPipeline:
             self._qsets[slot] = {k: torch.empty_like(v) for k, v in self._qsets[0].items()}
         return self._qsets[slot]
 
+    def own_rows(self, n: int) -> tuple[int, int, int]:
+        """(rows per slice, first row, end row) of the slice of an n-row batch this rank uploads and,
+        with result_rows="own", answers for."""
+        if self.world == 1:
+            return n, 0, n
+        per = (n + self.world - 1) // self.world
+        lo = min(self.rank * per, n)
+        return per, lo, min(lo + per, n)
+
     def load_queries(self, des, xy, angle, octave, frame, slot: int = 0, overlap: bool = False) -> int:
         """Copy one batch of query frames (host or device arrays) into query-buffer set `slot`.
         overlap=True issues the copies on the pipeline's copy stream, so that (with pinned host
         memory) they run while the kernels of the other set are busy; detect_device(n, slot) waits
-        for them on the device."""
+        for them on the device.  Database-sharded over several ranks with replicated_host: a HOST
+        batch is the same on every rank (the query is broadcast), so each rank uploads
+        rows [lo, hi) of it only and an all-gather over NVLink fills in the rest."""
         n = int(des.shape[0])
         if n > self.max_queries:
             raise ValueError("batch larger than max_queries")
         t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(a)  # noqa: E731
+        srcs = (("des", t(des)), ("xy", t(xy)), ("angle", t(angle)), ("octave", t(octave)), ("frame", t(frame)))
         q = self._qset(slot)
         if overlap and self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -220,9 +248,20 @@ class DetectionPipeline:
         if overlap:
             stream.wait_stream(torch.cuda.current_stream(self.device)) if self._consumed[slot] is None else \
                 stream.wait_event(self._consumed[slot])
+        sliced = (self.world > 1 and self.shard_mode == "db" and self.replicated_host and n > 0 and
+                  not any(a.is_cuda for _, a in srcs))
         with torch.cuda.stream(stream):
-            for key, src in (("des", des), ("xy", xy), ("angle", angle), ("octave", octave), ("frame", frame)):
-                q[key][:n].copy_(t(src), non_blocking=True)
+            if sliced:
+                import torch.distributed as dist
+                per, lo, hi = self.own_rows(n)
+                for key, src in srcs:
+                    q[key][lo:hi].copy_(src[lo:hi], non_blocking=True)
+                for key, _ in srcs:      # in place: this rank's slice already sits at its offset
+                    buf = q[key][:per * self.world]
+                    dist.all_gather_into_tensor(buf, buf[self.rank * per:(self.rank + 1) * per], group=self.group)
+            else:
+                for key, src in srcs:
+                    q[key][:n].copy_(src, non_blocking=True)
             if overlap:
                 self._loaded[slot] = torch.cuda.Event()
                 self._loaded[slot].record(stream)
@@ -240,7 +279,7 @@ class DetectionPipeline:
                                                                     qs["frame"])
         q = self.q_des[:n]
         merge = E.merge_top2_float if self.float_path else E.merge_top2
-        if self.seed_matcher is not None:
+        if self.seed_matcher is not None and n >= self.seed_min_queries:
             # Threshold seeding.  A shard-local sweep has to establish every query row's pruning threshold
             # from scratch - about 2 ln(rows) slow-path updates per row and SHARD, i.e. G times the
             # threshold work of one GPU holding the whole database.  Instead every rank sweeps the small
@@ -286,7 +325,7 @@ class DetectionPipeline:
         self._consumed[slot] = torch.cuda.Event()
         self._consumed[slot].record()
         return dict(idx=idx, d2=d2, dist=dist_f, ok=ok, match_q=mq, match_t=mt, n_matches=n_dev,
-                    hough=hough, affine=aff)
+                    hough=hough, affine=aff, n=n)
 
     # ---------------------------------------------------------------- host in, host out
     def detect(self, des, xy, angle, octave, frame) -> dict:
@@ -319,8 +358,11 @@ class DetectionPipeline:
         if ovf or ovf2:
             raise RuntimeError("output capacity exceeded")
         a = r["affine"]
+        # after the exchange every rank holds the merged lists of ALL query rows; with result_rows="own"
+        # a rank reads back only the rows of its slice (the same rows it uploaded)
+        _, lo, hi = self.own_rows(r["n"]) if self.result_rows == "own" else (0, 0, r["n"])
         out = dict(
-            idx=r["idx"].cpu().numpy(), ok=r["ok"].cpu().numpy(), n_matches=n_m, n_bins=n_bins,
+            idx=r["idx"][lo:hi].cpu().numpy(), ok=r["ok"][lo:hi].cpu().numpy(), row_lo=lo, n_matches=n_m, n_bins=n_bins,
             n_votes=n_votes, n_near_edge=n_edge, n_valid=n_valid,
             valid_bin=a.valid_bin[:n_valid].cpu().numpy(), params=a.params[:n_valid].cpu().numpy(),
             votes=a.votes[:n_valid].cpu().numpy(), status=a.status[:n_valid].cpu().numpy())

@@ -14,7 +14,17 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
 
 import bench  # noqa: E402
-from sod_b200.pipeline import DetectionPipeline, ModelDatabase  # noqa: E402
+from sod_b200.pipeline import DetectionPipeline  # noqa: E402
+
+
+def same(a: dict, b: dict, what: str) -> None:
+    """Two fetched results agree: match lists row by row, verified bins as sets (compaction order is free)."""
+    oa = np.lexsort((a["valid_code"], a["valid_group"]))
+    ob = np.lexsort((b["valid_code"], b["valid_group"]))
+    for k in ("idx", "ok"):
+        assert np.array_equal(a[k], b[k]), f"{what} changed {k}"
+    for k in ("valid_group", "valid_code", "votes", "status", "params"):
+        assert np.array_equal(a[k][oa], b[k][ob]), f"{what} changed {k}"
 
 
 def main():
@@ -27,22 +37,35 @@ def main():
     wl = bench.make_workload(args, dev)
     nq = args.frames * args.per_frame
     db = bench.make_database(wl)
-    q = (wl["q_des"], wl["q_xy"], wl["q_angle"], wl["q_octave"], wl["q_frame"])
-    sharded = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev).detect(*q)
-    # the same with threshold seeding forced on (it is automatic only for large databases): a replicated
-    # 1024-row sample, each rank seeds 1/G of the query rows, one min-reduce, then the shard sweep
+    q_dev = (wl["q_des"], wl["q_xy"], wl["q_angle"], wl["q_octave"], wl["q_frame"])
+    q = tuple(torch.as_tensor(a).cpu() for a in q_dev)    # HOST batch, the same on every rank
+    # host batch: every rank uploads its slice of the rows, an all-gather replicates it (load_queries)
+    pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev)
+    assert pipe.seed_matcher is None and pipe.spaces_per_frame == args.objects
+    sharded = pipe.detect(*q)
+    # device-resident batch (no slicing), and a host batch uploaded whole by every rank
+    same(sharded, pipe.detect(*q_dev), "device-resident inputs")
+    same(sharded, DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,
+                                    replicated_host=False).detect(*q), "whole-batch upload")
+    # the same with threshold seeding forced on (it is automatic only for large databases and batches): a
+    # replicated 1024-row sample, each rank seeds 1/G of the query rows, one min-reduce, then the shard sweep
     seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024)
+    seeded_pipe.seed_min_queries = 0
     assert seeded_pipe.seed_matcher is not None
     seeded = seeded_pipe.detect(*q)
     # and with the gather form of the exchange (all-gather of the lists + merge on every rank)
     gathered_lists = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,
                                        exchange="gather").detect(*q)
-    for other, what in ((seeded, "threshold seeding"), (gathered_lists, "the gather exchange")):
-        for k in ("idx", "ok", "valid_group", "valid_code", "votes", "status", "params"):
-            o1 = np.lexsort((sharded["valid_code"], sharded["valid_group"]))
-            o2 = np.lexsort((other["valid_code"], other["valid_group"]))
-            a, b = (sharded[k], other[k]) if k in ("idx", "ok") else (sharded[k][o1], other[k][o2])
-            assert np.array_equal(a, b), f"{what} changed {k}"
+    same(sharded, seeded, "threshold seeding")
+    same(sharded, gathered_lists, "the gather exchange")
+    # result_rows="own": every rank reads back only the rows of its slice; together they are the batch
+    own = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, result_rows="own").detect(*q)
+    _, lo, hi = pipe.own_rows(nq)
+    assert own["row_lo"] == lo and np.array_equal(own["idx"], sharded["idx"][lo:hi]) and \
+        np.array_equal(own["ok"], sharded["ok"][lo:hi])
+    # a small batch after a large one on the same pipeline (latency configuration: no seeding, same buffers)
+    small = pipe.detect(*(a[:1000] for a in q))
+    assert np.array_equal(small["idx"], sharded["idx"][:1000])
     keys = np.stack([sharded["valid_group"], sharded["valid_code"], sharded["votes"], sharded["status"] & 1], 1)
     params = sharded["params"]
     gathered_k = [None] * world
@@ -51,6 +74,7 @@ def main():
     dist.all_gather_object(gathered_p, params)
     if rank == 0:
         single = DetectionPipeline(db, nq, wl["frame_wh"], rank=0, world=1, device=dev).detect(*q)
+        assert single["row_lo"] == 0
         assert np.array_equal(sharded["idx"], single["idx"]), "match indices differ between 1 and G GPUs"
         assert np.array_equal(sharded["ok"], single["ok"])
         k1 = np.stack([single["valid_group"], single["valid_code"], single["votes"], single["status"] & 1], 1)
