@@ -477,7 +477,7 @@ def oracle_spot_check(wl, res, pipe, args, rows=64):
         table = O.hough_vote(scene, mq[own].tolist(), mt[own].tolist(), 15)
         vb = O.valid_bins(table, 5)
         live = O.affine_verify(scene, mq[own].tolist(), mt[own].tolist(), vb, 4)
-        want = sorted((int(b.pose[0]), tuple(int(v) for v in b.pose[1:]), int(b.votes)) for b in live)
+        want = sorted((int(b.group), tuple(int(v) for v in b.pose), int(b.votes)) for b in live)
         f0 = (res["valid_group"] // pipe.spaces_per_frame == 0) & ((res["status"] & 1) == 1)
         code = res["valid_code"][f0].astype(np.int64)
         got = sorted((int(g % pipe.spaces_per_frame), (int(c // 3375), int(c // 225 % 15), int(c // 15 % 15), int(c % 15)), int(v))
