@@ -215,8 +215,11 @@ typedef struct {
 typedef struct {
   double* pose;        /* [M][4] x, y, alpha, scale per match (estimate_object_pose) */
   uint32_t* base_bin;  /* [M] ix | iy<<8 | itheta<<16 | isigma<<24 (calculate_bin_index) */
-  uint8_t* near_edge;  /* [M] 1 if x, y or theta lies within 1e-9 of a bin boundary */
-  int32_t* counters;   /* [4] n_bins, n_votes, n_near_edge, overflow flag; zeroed by the call */
+  uint8_t* near_edge;  /* [M] 0; 1 = x*bins/W or y*bins/H lies within 1e-9 of an integer and the bin was
+                          confirmed for every admissible libm (cos / sin moved by +-4 ulp give the same
+                          bin, or the angle is exactly 0); 2 = those evaluations disagree */
+  int32_t* counters;   /* [8] n_bins, n_votes, n_near_edge (flags 1 and 2), overflow flag, n_unresolved
+                          (flag 2), 3 reserved; zeroed by the call */
   int32_t* bin_group;  /* [cap_bins] frame * groups_per_frame + image_group */
   int32_t* bin_code;   /* [cap_bins] ((ix*bins + iy)*bins + itheta)*bins + isigma */
   int32_t* bin_count;  /* [cap_bins] votes */
@@ -280,12 +283,15 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
 
 /* Outputs of sod_affine_verify (device), one entry per bin that entered with >= vote_threshold. */
 typedef struct {
-  int32_t* counters;    /* [2] n_valid, overflow; zeroed by the call */
+  int32_t* counters;    /* [4] n_valid, overflow, bins with a near-singular normal matrix, residual tests
+                           decided within 1e-9 relative + 1e-7 px of their limit; zeroed by the call */
   int32_t* valid_bin;   /* [cap_valid] index of the bin record */
   double* params;       /* [cap_valid][6] m1 m2 m3 m4 tx ty of the last fit */
   int32_t* votes;       /* [cap_valid] members left */
   int32_t* status;      /* [cap_valid] bit0 live (votes >= affine_threshold at the fixed point),
-                           bit1 near-singular normal matrix, bits 8.. number of passes */
+                           bit1 near-singular normal matrix (smallest |eigenvalue| <= 1e-10 x largest) in
+                           some pass, bit2 a residual test of the bin was decided on the edge of its
+                           limit, bits 8.. number of passes */
   uint8_t* member_keep; /* [cap_votes] aligned with sod_hough_out.members: 1 = still in its bin */
   int64_t cap_valid;
   int64_t cap_votes;    /* elements of member_keep: a bin whose members end past it is not verified and

@@ -111,6 +111,14 @@ __device__ __forceinline__ int solve_affine(double sxx, double sxy, double sx, d
 
 constexpr int kSmallAffine = 32;  // bins up to this size are verified by a single thread
 
+// remove_outliers keeps a pair unless |u_AP - u| > x_ref or |v_AP - v| > y_ref (AffineParameters.py:152).
+// The fitted parameters agree with numpy's pinv to ~1e-12 relative on well-conditioned bins (more on
+// near-singular ones), so a residual this close to its limit could be decided the other way by the
+// reference; such decisions are counted (counters[3], status bit 2), never altered.
+__device__ __forceinline__ bool residual_on_edge(double du, double dv, double x_ref, double y_ref) {
+  return fabs(du - x_ref) <= 1e-9 * x_ref + 1e-7 || fabs(dv - y_ref) <= 1e-9 * y_ref + 1e-7;
+}
+
 // One THREAD per small valid bin (the vast majority: random bins with 5-10 votes): the alive set is
 // a 32-bit mask, every pass re-gathers the coordinates of the alive pairs.
 __global__ void affine_verify_small_kernel(const AffineArgs a) {
@@ -137,7 +145,7 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
     const double y_ref = a.factor_y > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor_y) : inf;
     const int32_t* mem = a.members + off;
     unsigned alive = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-    int n_alive = cnt, passes = 0, live = 0, singular = 0;
+    int n_alive = cnt, passes = 0, live = 0, singular = 0, on_edge = 0;
     double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
     while (true) {
       double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0, sn = 0;
@@ -159,7 +167,9 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
         const double x = pm.x, y = pm.y;
         const double ua = __dadd_rn(__dadd_rn(__dmul_rn(pu[0], x), __dmul_rn(pu[1], y)), pu[2]);
         const double va = __dadd_rn(__dadd_rn(__dmul_rn(pv[0], x), __dmul_rn(pv[1], y)), pv[2]);
-        if (fabs(ua - static_cast<double>(pq.x)) > x_ref || fabs(va - static_cast<double>(pq.y)) > y_ref) {
+        const double du = fabs(ua - static_cast<double>(pq.x)), dv = fabs(va - static_cast<double>(pq.y));
+        on_edge += residual_on_edge(du, dv, x_ref, y_ref) ? 1 : 0;
+        if (du > x_ref || dv > y_ref) {
           alive &= ~(1u << j);
           ++removed;
         }
@@ -175,7 +185,9 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
     double* p = a.out.params + v * 6;
     p[0] = pu[0]; p[1] = pu[1]; p[2] = pv[0]; p[3] = pv[1]; p[4] = pu[2]; p[5] = pv[2];
     a.out.votes[v] = n_alive;
-    a.out.status[v] = live | (singular << 1) | (passes << 8);
+    a.out.status[v] = live | (singular << 1) | ((on_edge ? 1 : 0) << 2) | (passes << 8);
+    if (singular) atomicAdd(&a.out.counters[2], 1);
+    if (on_edge) atomicAdd(&a.out.counters[3], on_edge);
   }
 }
 
@@ -215,7 +227,7 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
     const int32_t* mem = a.members + off;
     for (int j = lane; j < cnt; j += 32) keep[j] = 1;
     __syncwarp();
-    int alive = cnt, passes = 0, live = 0, singular = 0;
+    int alive = cnt, passes = 0, live = 0, singular = 0, on_edge = 0;
     double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
     while (true) {
       double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0, sn = 0;
@@ -241,7 +253,9 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
         const double x = pm.x, y = pm.y;
         const double ua = __dadd_rn(__dadd_rn(__dmul_rn(pu[0], x), __dmul_rn(pu[1], y)), pu[2]);
         const double va = __dadd_rn(__dadd_rn(__dmul_rn(pv[0], x), __dmul_rn(pv[1], y)), pv[2]);
-        if (fabs(ua - static_cast<double>(pq.x)) > x_ref || fabs(va - static_cast<double>(pq.y)) > y_ref) {
+        const double du = fabs(ua - static_cast<double>(pq.x)), dv = fabs(va - static_cast<double>(pq.y));
+        on_edge += residual_on_edge(du, dv, x_ref, y_ref) ? 1 : 0;
+        if (du > x_ref || dv > y_ref) {
           keep[j] = 0;
           ++removed;
         }
@@ -255,11 +269,15 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
       if (removed == 0) { live = 1; break; }
       if (a.max_passes > 0 && passes >= a.max_passes) { live = 1; break; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) on_edge += __shfl_xor_sync(0xffffffffu, on_edge, o);
     if (lane == 0) {
       double* p = a.out.params + v * 6;
       p[0] = pu[0]; p[1] = pu[1]; p[2] = pv[0]; p[3] = pv[1]; p[4] = pu[2]; p[5] = pv[2];
       a.out.votes[v] = alive;
-      a.out.status[v] = live | (singular << 1) | (passes << 8);
+      a.out.status[v] = live | (singular << 1) | ((on_edge ? 1 : 0) << 2) | (passes << 8);
+      if (singular) atomicAdd(&a.out.counters[2], 1);
+      if (on_edge) atomicAdd(&a.out.counters[3], on_edge);
     }
   }
 }
@@ -309,7 +327,7 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
                     hough->bin_count && hough->bin_offset && hough->members,
                 "null input array");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SOD_CHECK_CUDA(cudaMemsetAsync(out->counters, 0, 2 * sizeof(int32_t), st));
+  SOD_CHECK_CUDA(cudaMemsetAsync(out->counters, 0, 4 * sizeof(int32_t), st));
   const int sms = device_sm_count();
   if (sms <= 0) return SOD_ERR_CUDA;
   AffineArgs a;

@@ -33,10 +33,36 @@ __device__ __forceinline__ int sext8(int v) {
 }
 
 // Near a truncation boundary?  cos/sin on the device may differ from the host libm in the last
-// bit; only values this close to an integer could then land in another bin.
+// bits; only values this close to an integer could then land in another bin.
 __device__ __forceinline__ bool near_integer(double f) {
   const double r = rint(f);
   return fabs(f - r) <= 1e-9 * fmax(1.0, fabs(f));
+}
+
+// v moved by `ulps` units in the last place, away from (ulps > 0) or towards (ulps < 0) zero.
+__device__ __forceinline__ double step_ulps(double v, int ulps) {
+  return __longlong_as_double(__double_as_longlong(v) + ulps);
+}
+
+// x, y of estimate_object_pose and their truncated bin coordinates for given cos / sin values, in the
+// reference's operation order (HoughTransformHelperFunctions.py:28-32, 49-57).
+struct XyBins {
+  double x, y, fx, fy;
+  int tx, ty;  // int(x*bins/W), int(y*bins/H) before the -1 shift and the clamp
+};
+__device__ __forceinline__ XyBins xy_bins(double ca, double sa, double tx, double ty, double qx, double qy,
+                                          double bx, double by, double W, double H) {
+  XyBins r;
+  const double rx = __dsub_rn(__dmul_rn(ca, tx), __dmul_rn(sa, ty));
+  const double ry = __dadd_rn(__dmul_rn(sa, tx), __dmul_rn(ca, ty));
+  r.x = __dadd_rn(rx, qx);
+  r.y = __dadd_rn(ry, qy);
+  r.fx = __ddiv_rn(__dmul_rn(r.x, bx), W);
+  r.fy = __ddiv_rn(__dmul_rn(r.y, by), H);
+  // int() truncates toward zero; clamp before converting so huge poses stay defined
+  r.tx = static_cast<int>(fmin(fmax(trunc(r.fx), -1.0e6), 1.0e6));
+  r.ty = static_cast<int>(fmin(fmax(trunc(r.fy), -1.0e6), 1.0e6));
+  return r;
 }
 
 // Bin counts of the four pose dimensions (x, y, theta, log2 scale).  The live path uses one count
@@ -93,30 +119,44 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
     al = fmod(__dadd_rn(al, kTwoPi), kTwoPi);  // operand is > 0: Python's % equals fmod here
     if (al < 0.0) al = __dadd_rn(al, kTwoPi);
     const double ca = cos(al), sa = sin(al);
-    const double rx = __dsub_rn(__dmul_rn(ca, tx), __dmul_rn(sa, ty));
-    const double ry = __dadd_rn(__dmul_rn(sa, tx), __dmul_rn(ca, ty));
-    const double x = __dadd_rn(rx, static_cast<double>(qp.x));
-    const double y = __dadd_rn(ry, static_cast<double>(qp.y));
+    const double qx = static_cast<double>(qp.x), qy = static_cast<double>(qp.y);
+    const double bx = static_cast<double>(bins.x), by = static_cast<double>(bins.y);
+    const XyBins c = xy_bins(ca, sa, tx, ty, qx, qy, bx, by, W, H);
     double* po = a.pose + i * 4;
-    po[0] = x; po[1] = y; po[2] = al; po[3] = s;
+    po[0] = c.x; po[1] = c.y; po[2] = al; po[3] = s;
 
-    const double fx = __ddiv_rn(__dmul_rn(x, static_cast<double>(bins.x)), W);
-    const double fy = __ddiv_rn(__dmul_rn(y, static_cast<double>(bins.y)), H);
+    // theta and sigma bins depend on exact IEEE operations only (no libm): always bit-identical
     const double ft = fmod(__ddiv_rn(__dmul_rn(al, static_cast<double>(bins.t)), kTwoPi),
                            static_cast<double>(bins.t));
-    // int() truncates toward zero; clamp before converting so huge poses stay defined
-    int ix = static_cast<int>(fmin(fmax(trunc(fx), -1.0e6), 1.0e6));
-    int iy = static_cast<int>(fmin(fmax(trunc(fy), -1.0e6), 1.0e6));
-    ix = min(max(0, ix - 1), bins.x - 1);
-    iy = min(max(0, iy - 1), bins.y - 1);
+    const int ix = min(max(0, c.tx - 1), bins.x - 1);
+    const int iy = min(max(0, c.ty - 1), bins.y - 1);
     const int it = static_cast<int>(ft);
     const int kk = min(max(k, SOD_SIGMA_LUT_MIN), SOD_SIGMA_LUT_MIN + SOD_SIGMA_LUT_LEN - 1);
     const int is = a.sigma_lut[kk - SOD_SIGMA_LUT_MIN];
     a.base_bin[i] = static_cast<uint32_t>(ix) | (static_cast<uint32_t>(iy) << 8) |
                     (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
-    const bool edge = near_integer(fx) || near_integer(fy) || near_integer(ft);
-    if (a.near_edge) a.near_edge[i] = edge ? 1 : 0;
-    if (edge && a.counters) atomicAdd(&a.counters[2], 1);
+    // x and y go through cos / sin, whose last bits may differ between the device and the host libm
+    // (CUDA: <= 2 ulp, glibc: < 1 ulp).  A match whose x*bins/W or y*bins/H lies within 1e-9 of an
+    // integer is RESOLVED on the spot: the truncations are re-evaluated with cos and sin moved by
+    // +-4 ulp (x and y are monotone in each, so the four corners bound every admissible libm); if all
+    // agree, the bin is the reference's whatever its libm returns.  al == 0 is exact everywhere
+    // (cos = 1, sin = 0).  Only a disagreement is left open; it is counted in counters[4].
+    int edge = (near_integer(c.fx) || near_integer(c.fy)) ? 1 : 0;
+    if (edge && al != 0.0) {
+      bool same = true;
+#pragma unroll
+      for (int corner = 0; corner < 4; ++corner) {
+        const XyBins p = xy_bins(step_ulps(ca, (corner & 1) ? 4 : -4), step_ulps(sa, (corner & 2) ? 4 : -4), tx, ty,
+                                 qx, qy, bx, by, W, H);
+        same = same && min(max(0, p.tx - 1), bins.x - 1) == ix && min(max(0, p.ty - 1), bins.y - 1) == iy;
+      }
+      if (!same) edge = 2;
+    }
+    if (a.near_edge) a.near_edge[i] = static_cast<uint8_t>(edge);
+    if (edge && a.counters) {
+      atomicAdd(&a.counters[2], 1);
+      if (edge == 2) atomicAdd(&a.counters[4], 1);
+    }
     if (a.group_of) {
       a.group_of[i] = grp;
       atomicAdd(&a.group_count[grp], 1);
@@ -675,7 +715,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   }
   SOD_CHECK_ARG(out->counters, "null counters");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SOD_CHECK_CUDA(cudaMemsetAsync(out->counters, 0, 4 * sizeof(int32_t), st));
+  SOD_CHECK_CUDA(cudaMemsetAsync(out->counters, 0, 8 * sizeof(int32_t), st));
   if (n_matches == 0) return SOD_OK;
   const int64_t n_groups = static_cast<int64_t>(scene->n_frames) * scene->groups_per_frame;
   SOD_CHECK_ARG(scene->n_frames >= 1 && scene->groups_per_frame >= 1 && n_groups < (int64_t(1) << 30),

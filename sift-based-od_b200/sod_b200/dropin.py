@@ -141,7 +141,7 @@ class _PairBatch:
         h.cap_bins = nb
         h.cap_votes = max(total, 1)
         h.pose = h.base_bin = h.near_edge = h.bin_order = h.bin_mean = None
-        h.counters = torch.tensor([self.n_bins, total, 0, 0], dtype=torch.int32, device=dev)
+        h.counters = torch.tensor([self.n_bins, total, 0, 0, 0, 0, 0, 0], dtype=torch.int32, device=dev)
         h.bin_group = torch.zeros(nb, dtype=torch.int32, device=dev)
         h.bin_code = torch.tensor([int(b.pose[3]) for b in bins_list] or [0], dtype=torch.int32, device=dev)
         h.bin_count = torch.tensor(counts or [0], dtype=torch.int32, device=dev)

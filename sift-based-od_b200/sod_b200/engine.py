@@ -401,7 +401,7 @@ class HoughResult:
         self.pose = e((max(m_cap, 1), 4), torch.float64)
         self.base_bin = e(max(m_cap, 1), torch.int32)
         self.near_edge = e(max(m_cap, 1), torch.uint8)
-        self.counters = torch.zeros(4, dtype=torch.int32, device=device)
+        self.counters = torch.zeros(8, dtype=torch.int32, device=device)
         self.bin_group = e(self.cap_bins, torch.int32)
         self.bin_code = e(self.cap_bins, torch.int32)
         self.bin_count = e(self.cap_bins, torch.int32)
@@ -424,7 +424,7 @@ class HoughResult:
         nb, nv = int(c[0]), int(c[1])
         order = torch.argsort(self.bin_order[:nb])
         g = lambda t: t[:nb][order].cpu().numpy()  # noqa: E731
-        return dict(n_bins=nb, n_votes=nv, n_near_edge=int(c[2]), rec=order.cpu().numpy(),
+        return dict(n_bins=nb, n_votes=nv, n_near_edge=int(c[2]), n_unresolved_edge=int(c[4]), rec=order.cpu().numpy(),
                     group=g(self.bin_group), code=g(self.bin_code), count=g(self.bin_count),
                     offset=g(self.bin_offset), mean=g(self.bin_mean), order_key=g(self.bin_order),
                     members=self.members[:nv].cpu().numpy())
@@ -482,7 +482,7 @@ class AffineResult:
         self.cap_valid = max(1, hough.cap_bins if vote_threshold <= 0 else
                              min(hough.cap_bins, hough.cap_votes // vote_threshold))
         self.cap_votes = hough.cap_votes
-        self.counters = torch.zeros(2, dtype=torch.int32, device=device)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=device)
         self.valid_bin = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
         self.params = torch.empty((self.cap_valid, 6), dtype=torch.float64, device=device)
         self.votes = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
@@ -501,7 +501,9 @@ class AffineResult:
         st = self.status[:nv].cpu().numpy()
         return dict(n_valid=nv, valid_bin=self.valid_bin[:nv].cpu().numpy(),
                     params=self.params[:nv].cpu().numpy(), votes=self.votes[:nv].cpu().numpy(),
-                    live=(st & 1).astype(bool), singular=((st >> 1) & 1).astype(bool), passes=st >> 8,
+                    live=(st & 1).astype(bool), singular=((st >> 1) & 1).astype(bool),
+                    residual_edge=((st >> 2) & 1).astype(bool), passes=st >> 8,
+                    n_singular=int(c[2]), n_residual_edge=int(c[3]),
                     member_keep=self.member_keep[:n_votes].cpu().numpy().astype(bool))
 
 

@@ -354,7 +354,8 @@ class DetectionPipeline:
     def fetch(self, r: dict) -> dict:
         """Device -> host read of one result: matches, counters, verified bins of this rank."""
         counters = torch.cat([r["n_matches"], r["hough"].counters, r["affine"].counters]).cpu().numpy()
-        n_m, n_bins, n_votes, n_edge, ovf, n_valid, ovf2 = (int(v) for v in counters)
+        n_m, n_bins, n_votes, n_edge, ovf, n_open = (int(v) for v in counters[:6])
+        n_valid, ovf2, n_singular, n_res_edge = (int(v) for v in counters[9:13])
         if ovf or ovf2:
             raise RuntimeError("output capacity exceeded")
         a = r["affine"]
@@ -363,7 +364,8 @@ class DetectionPipeline:
         _, lo, hi = self.own_rows(r["n"]) if self.result_rows == "own" else (0, 0, r["n"])
         out = dict(
             idx=r["idx"][lo:hi].cpu().numpy(), ok=r["ok"][lo:hi].cpu().numpy(), row_lo=lo, n_matches=n_m, n_bins=n_bins,
-            n_votes=n_votes, n_near_edge=n_edge, n_valid=n_valid,
+            n_votes=n_votes, n_near_edge=n_edge, n_unresolved_edge=n_open, n_valid=n_valid,
+            n_singular=n_singular, n_residual_edge=n_res_edge,
             valid_bin=a.valid_bin[:n_valid].cpu().numpy(), params=a.params[:n_valid].cpu().numpy(),
             votes=a.votes[:n_valid].cpu().numpy(), status=a.status[:n_valid].cpu().numpy())
         h = r["hough"]
@@ -397,4 +399,4 @@ class DetectionPipeline:
 
     @staticmethod
     def fetched_bytes(out: dict) -> int:
-        return int(sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) + 7 * 4)
+        return int(sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) + 13 * 4)

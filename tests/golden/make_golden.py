@@ -176,9 +176,99 @@ def make_postprocess():
           "sub-clusters", len(subs))
 
 
+def singular_bins(seed=31):
+    """Bins for the affine stage that the Hough fixtures never produce: duplicate
+    model locations (real SIFT emits several orientations at one location, main.py:43), collinear
+    model points, exactly-threshold sizes, ill-conditioned normal matrices from cond ~1e7 to ~1e11, and
+    well-conditioned controls.  -> list of dicts(name, model_xy f32 [n,2], query_xy f32 [n,2], isigma)."""
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: np.asarray(a, np.float32)  # noqa: E731
+    sim = lambda m, s, th, t, noise: (s * (m @ np.array([[np.cos(th), np.sin(th)], [-np.sin(th), np.cos(th)]])) + t  # noqa: E731
+                                      + rng.normal(0, noise, m.shape))
+    out = []
+    for k in range(4):
+        m = rng.uniform(0, 1500, (7, 2))
+        out.append(dict(name=f"generic{k}", model=f32(m), query=f32(sim(m, 2.0, 0.3 * k, [900, 700], 2.0)), isigma=2))
+    for k in range(4):                                   # 2 distinct model locations among 5..8 pairs (rank 2)
+        base = rng.uniform(100, 1400, (2, 2))
+        idx = np.array([0, 1, 0, 0, 1, 1, 0, 1][:5 + k])
+        m = base[idx]
+        out.append(dict(name=f"two_locations{k}", model=f32(m), query=f32(sim(m, 1.0, 0.5, [300, 200], 1.5)), isigma=2))
+    for k in range(3):                                   # a single model location (rank 1)
+        m = np.tile(rng.uniform(100, 1400, (1, 2)), (5 + k, 1))
+        out.append(dict(name=f"one_location{k}", model=f32(m), query=f32(sim(m, 1.0, 0.0, [50, 60], 1.0)), isigma=1))
+    for k in range(3):                                   # exactly collinear integer model points (rank 2)
+        m = np.array([[100 + 10 * j * (k + 1), 200 + 20 * j * (k + 1)] for j in range(6)], float)
+        out.append(dict(name=f"collinear_int{k}", model=f32(m), query=f32(sim(m, 1.5, 0.2, [400, 100], 1.0)), isigma=2))
+    for k in range(3):                                   # collinear up to float32 rounding
+        t = rng.uniform(0, 1, (6, 1))
+        m = np.array([100.0, 200.0]) + t * np.array([700.0, 300.0 + 50 * k])
+        out.append(dict(name=f"collinear_f32_{k}", model=f32(m), query=f32(sim(m, 0.5, 1.0, [800, 900], 0.5)), isigma=1))
+    for eps in (1e-2, 1e-3, 1e-4, 1e-5, 1e-6):          # near-collinear: cond(S) from ~1e7 up to ~1e11
+        for k in range(2):
+            m = np.array([[100 + 10 * j, 200 + 20 * j] for j in range(6)], float) + 1000 * eps * rng.normal(0, 1, (6, 2))
+            out.append(dict(name=f"near_collinear_{eps:g}_{k}", model=f32(m),
+                            query=f32(sim(m, 1.0, 0.1, [200, 300], 0.5)), isigma=2))
+    # sizes around the threshold (4): exactly 4 good pairs; 5 pairs of which one is a gross outlier (4 stay);
+    # 5 pairs with two gross outliers (3 stay -> the bin dies)
+    m = rng.uniform(0, 1500, (4, 2))
+    out.append(dict(name="exactly_threshold", model=f32(m), query=f32(sim(m, 1.0, 0.4, [500, 500], 0.5)), isigma=2))
+    for n_out in (1, 2):
+        m = rng.uniform(0, 1500, (5, 2))
+        q = sim(m, 1.0, 0.4, [500, 500], 0.5)
+        q[:n_out] += [[900.0, -700.0], [-800.0, 600.0]][:n_out]
+        out.append(dict(name=f"outliers{n_out}_of5", model=f32(m), query=f32(q), isigma=2))
+    # sigma bin 0 (every scale factor <= 1, SURVEY Q4): the residual limits are 0, everything is dropped
+    m = rng.uniform(0, 1500, (6, 2))
+    out.append(dict(name="isigma0", model=f32(m), query=f32(sim(m, 1.0, 0.2, [100, 100], 1.0)), isigma=0))
+    return out
+
+
+def make_affine_singular(width=4032, height=3024, threshold=4):
+    """tests/golden/affine_singular.npz: the reference's AffineParameters / remove_outliers /
+    Main.apply_affine_parameters on the bins above, bin by bin (the loop is an independent fixed point
+    per bin) and all together."""
+    import cv2
+    refmain = import_reference()
+    from PoseBin import PoseBin as RefPoseBin  # the reference's class
+    cases = singular_bins()
+    kp = lambda p: cv2.KeyPoint(float(p[0]), float(p[1]), 1.0)  # noqa: E731
+    bins = []
+    for c in cases:
+        pairs = [(kp(m), kp(q)) for m, q in zip(c["model"], c["query"])]
+        bins.append(RefPoseBin((0, 0, 0, int(c["isigma"])), (1500, 1000), len(pairs), pairs, (0.0, 0.0, 0.0, 1.0)))
+    first = []
+    for b in bins:                                       # one AffineParameters call on the untouched bin
+        from AffineParameters import AffineParameters as ref_fit
+        ref_fit(b)
+        first.append([float(v) for v in b.affine_parameters])
+    tags = [[id(p[0]) for p in b.keypoint_pairs] for b in bins]
+    m = refmain.Main()
+    m.image_query_size = (width, height)
+    m.valid_bins = list(bins)
+    m.apply_affine_parameters(threshold)
+    live = [any(b is v for v in m.valid_bins) for b in bins]
+    keep_off, keep = [0], []
+    for b, t in zip(bins, tags):
+        alive = {id(p[0]) for p in b.keypoint_pairs}
+        keep += [i in alive for i in t]
+        keep_off.append(len(keep))
+    off = np.cumsum([0] + [len(c["model"]) for c in cases])
+    np.savez_compressed(
+        HERE / "affine_singular.npz", names=np.array([c["name"] for c in cases]), off=off,
+        model=np.concatenate([c["model"] for c in cases]), query=np.concatenate([c["query"] for c in cases]),
+        isigma=np.array([c["isigma"] for c in cases], np.int32), width=np.int32(width), height=np.int32(height),
+        threshold=np.int32(threshold), first_params=np.array(first, np.float64),
+        last_params=np.array([[float(v) for v in b.affine_parameters] for b in bins], np.float64),
+        votes=np.array([b.votes for b in bins], np.int32), live=np.array(live), keep=np.array(keep))
+    print("affine_singular:", len(cases), "bins,", int(np.sum(live)), "live,", int(np.sum(keep)), "of", len(keep), "pairs kept")
+
+
 def main():
     if "--postprocess-only" in sys.argv:
         return make_postprocess()
+    if "--affine-singular-only" in sys.argv:
+        return make_affine_singular()
     refmain = import_reference()
     import cv2
     for name, kw in SCENES.items():
@@ -191,6 +281,7 @@ def main():
               len(out["valid_keys"]), "live", len(out["live_keys"]), "final", len(out["final_pose"]))
 
     make_postprocess()
+    make_affine_singular()
 
     # known-answer facts taken from the reference's own libraries
     import math

@@ -102,3 +102,32 @@ def test_c5_hough_stress_2m_matches_bin_counts():
         assert (np.diff(m) > 0).all()
     a = aff.host(nv)
     assert a["live"].sum() >= 400            # ~one verified bin per object at least
+    # The affine stage at stress size against the oracle, object by object, on a sample of 50 objects
+    # (every 10th): the bins that survive Main.apply_affine_parameters, their votes and their member
+    # lists must be the oracle's; parameters within the north star's 1e-4.
+    assert c[4] == 0 and a["n_residual_edge"] == 0     # nothing was decided on an edge: parity is unconditional
+    grp_of_match = d["img_group"][d["m_image"][d["match_t"]]]
+    rec_group = res.bin_group[:nb].cpu().numpy()
+    rec_code = res.bin_code[:nb].cpu().numpy()
+    cnt = res.bin_count[:nb].cpu().numpy()
+    keep = a["member_keep"]
+    by_key = {}
+    for v, rec in enumerate(a["valid_bin"]):
+        if a["live"][v]:
+            by_key[(int(rec_group[rec]), int(rec_code[rec]))] = (v, int(rec))
+    checked = 0
+    for obj in range(0, 500, 10):
+        ids = np.flatnonzero(grp_of_match == obj)
+        table = O.hough_vote(osc, d["match_q"][ids], d["match_t"][ids], bins)
+        live = O.affine_verify(osc, d["match_q"][ids], d["match_t"][ids], O.valid_bins(table, 5), 4)
+        want = {(obj, ((b.pose[0] * bins + b.pose[1]) * bins + b.pose[2]) * bins + b.pose[3]): b for b in live}
+        got = {k: v for k, v in by_key.items() if k[0] == obj}
+        assert set(got) == set(want), f"object {obj}: surviving bins differ"
+        for k, b in want.items():
+            v, rec = got[k]
+            assert a["votes"][v] == b.votes
+            m = mem[off[rec]:off[rec] + cnt[rec]][keep[off[rec]:off[rec] + cnt[rec]]]
+            np.testing.assert_array_equal(m, ids[b.members])
+            np.testing.assert_allclose(a["params"][v], b.affine, rtol=1e-4, atol=1e-6)
+            checked += 1
+    assert checked >= 50

@@ -199,3 +199,157 @@ def test_too_many_counters_is_rejected_loudly():
     z = np.load(GOLD / "scene_tiny.npz")
     with pytest.raises(_capi.SodError):
         E.HoughVoter(_scene_arrays(z), (30, 30, 15, 15))
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: rank-deficient bins, edge cases of the truncations and of the residual test
+# ------------------------------------------------------------------------------------------------
+def _pair_batch(z):
+    """The fixture's bins as the degenerate Hough output the drop-in uses for caller-built PoseBins."""
+    import cv2
+    from PoseBin import PoseBin
+    from sod_b200 import dropin
+    kp = lambda p: cv2.KeyPoint(float(p[0]), float(p[1]), 1.0)  # noqa: E731
+    off = z["off"]
+    bins = []
+    for b in range(len(z["names"])):
+        pairs = [(kp(m), kp(q)) for m, q in zip(z["model"][off[b]:off[b + 1]], z["query"][off[b]:off[b + 1]])]
+        bins.append(PoseBin((0, 0, 0, int(z["isigma"][b])), (1500, 1000), len(pairs), pairs, (0.0, 0.0, 0.0, 1.0)))
+    return dropin._PairBatch(bins, int(z["width"]), int(z["height"])), bins
+
+
+def _by_bin(a, n_bins):
+    """AffineResult.host() rows re-ordered by bin record."""
+    pos = np.empty(n_bins, np.int64)
+    pos[a["valid_bin"]] = np.arange(len(a["valid_bin"]))
+    return pos
+
+
+def test_affine_rank_deficient_and_ill_conditioned_bins_equal_reference():
+    """tests/golden/affine_singular.npz (the reference's own AffineParameters / apply_affine_parameters on
+    bins with duplicate model locations, collinear points, cond(S) up to ~1e11, sizes at the threshold,
+    sigma bin 0): identical survivor sets, votes and live flags; parameters within 1e-4 relative
+    (north star) of numpy's pinv solution - minimum-norm on the rank-deficient bins; the
+    near-singular status bit marks exactly the bins whose normal matrix is rank deficient."""
+    from sod_b200 import engine as E
+    z = np.load(GOLD / "affine_singular.npz")
+    batch, bins = _pair_batch(z)
+    n = len(bins)
+    off = z["off"]
+    # one fit, no pruning (AffineParameters(posebin))
+    res = E.affine_verify(batch.scene, batch.ids, batch.ids, batch.h, vote_threshold=0, affine_threshold=0,
+                          factor=0.0, factor_y=0.0, max_passes=1)
+    a = res.host(batch.total)
+    pos = _by_bin(a, n)
+    scale = np.abs(z["first_params"]).max(1, keepdims=True)
+    err = np.abs(a["params"][pos] - z["first_params"]) / scale
+    assert err.max() < 1e-4, (z["names"][err.max(1).argmax()], err.max())
+    well = np.array([nm.startswith(("generic", "exactly", "outliers", "isigma", "near_collinear_0.01", "near_collinear_0.001"))
+                     for nm in z["names"]])
+    assert err[well].max() < 1e-9                       # well-conditioned bins agree far below the bar
+    deficient = np.array([nm.startswith(("two_locations", "one_location", "collinear_")) for nm in z["names"]])
+    np.testing.assert_array_equal(a["singular"][pos][deficient], True)
+    np.testing.assert_array_equal(a["singular"][pos][well], False)
+    assert a["n_singular"] == int(a["singular"].sum()) >= int(deficient.sum())
+    # the whole fixed point (Main.apply_affine_parameters, factor 128 = pos_factor * 4)
+    res = E.affine_verify(batch.scene, batch.ids, batch.ids, batch.h, vote_threshold=0,
+                          affine_threshold=int(z["threshold"]), factor=128.0, factor_y=128.0)
+    a = res.host(batch.total)
+    pos = _by_bin(a, n)
+    np.testing.assert_array_equal(a["live"][pos], z["live"])
+    np.testing.assert_array_equal(a["votes"][pos], z["votes"])
+    np.testing.assert_array_equal(a["member_keep"][:batch.total], z["keep"])
+    err = np.abs(a["params"][pos] - z["last_params"]) / np.abs(z["last_params"]).max(1, keepdims=True)
+    assert err.max() < 1e-4, (z["names"][err.max(1).argmax()], err.max())
+    # the oracle on the same bins gives the same answer as the fixture (CPU test) - and as the device:
+    for b in (int(np.flatnonzero(deficient)[0]), int(np.flatnonzero(deficient)[-1])):
+        fit = np.asarray(O.affine_fit([tuple(map(float, r)) for r in z["model"][off[b]:off[b + 1]]],
+                                      [tuple(map(float, r)) for r in z["query"][off[b]:off[b + 1]]]))
+        np.testing.assert_array_equal(fit, z["first_params"][b])
+
+
+def test_residual_decisions_on_the_edge_of_their_limit_are_counted():
+    """Exact-fit bins with a limit of 0 px (sigma bin 0): residuals are rounding noise (~1e-13) against
+    a limit of 0, the one situation in which a pair's fate depends on the last bits of the solver.
+    The device counts those decisions (sod_affine_out.counters[3], status bit 2) instead of hiding them."""
+    import cv2
+    from PoseBin import PoseBin
+    from sod_b200 import dropin, engine as E
+    kp = lambda x, y: cv2.KeyPoint(float(x), float(y), 1.0)  # noqa: E731
+    pts = [(0, 0), (100, 0), (0, 100), (100, 100), (50, 25), (20, 80)]
+    exact = PoseBin((0, 0, 0, 0), (100, 100), 6, [(kp(x, y), kp(2 * x + 10, 2 * y - 5)) for x, y in pts], (0, 0, 0, 1))
+    rng = np.random.default_rng(3)
+    noisy = PoseBin((0, 0, 0, 2), (100, 100), 6, [(kp(x, y), kp(2 * x + 10 + rng.normal(), 2 * y - 5 + rng.normal()))
+                                                  for x, y in pts], (0, 0, 0, 1))
+    batch = dropin._PairBatch([exact, noisy], 1280, 960)
+    a = E.affine_verify(batch.scene, batch.ids, batch.ids, batch.h, vote_threshold=0, affine_threshold=4,
+                        factor=128.0, factor_y=128.0).host(batch.total)
+    pos = _by_bin(a, 2)
+    assert a["residual_edge"][pos].tolist() == [True, False]
+    assert a["n_residual_edge"] >= 6
+    assert a["live"][pos][1] and a["votes"][pos][1] == 6
+
+
+def _boundary_scene(seed=9, n=600, width=1500, height=900, bins=15):
+    """Matches whose pose lands EXACTLY on bin boundaries: equal angles (alpha = 0: cos = 1, sin = 0 on
+    every libm) and integer coordinates chosen so that x * bins / W and y * bins / H are integers, among
+    generic matches, plus generic-angle matches nudged to within ~1e-7 of a boundary (the query x is a
+    float32, so that is the closest a real keypoint gets)."""
+    rng = np.random.default_rng(seed)
+    cent = np.array([[50.0, 40.0]])
+    m_xy = rng.integers(0, 100, (n, 2)).astype(np.float32)
+    m_angle = rng.uniform(0, 360, n).astype(np.float32)
+    m_oct = np.zeros(n, np.int64)
+    q_oct = rng.integers(0, 2, n)
+    q_angle = m_angle.copy()
+    q_xy = np.zeros((n, 2), np.float32)
+    s = 2.0 ** (q_oct - m_oct)
+    tx, ty = (cent[0, 0] - m_xy[:, 0]) * s, (cent[0, 1] - m_xy[:, 1]) * s
+    bx = rng.integers(-1, bins + 1, n) * (width // bins)          # includes x < 0 and x = W (SURVEY Q2/Q3)
+    by = rng.integers(-1, bins + 1, n) * (height // bins)
+    q_xy[:, 0], q_xy[:, 1] = bx - tx, by - ty                     # alpha = 0: x = tx + qx exactly
+    generic = rng.random(n) < 0.4
+    q_angle[generic] = rng.uniform(0, 360, int(generic.sum())).astype(np.float32)
+    q_xy[generic] = np.stack([rng.uniform(0, width, int(generic.sum())), rng.uniform(0, height, int(generic.sum()))], 1)
+    scene = O.Scene(q_xy, q_angle, scenes.pack_octave(q_oct, np.ones(n, np.int64)), m_xy, m_angle,
+                    scenes.pack_octave(m_oct, np.ones(n, np.int64)), np.zeros(n, np.int32), cent,
+                    np.array([[100, 80]]), width, height)
+    # generic-angle matches moved next to a boundary: pick the float32 qx that brings x closest to k * W / bins
+    near = np.flatnonzero(generic)[:150]
+    for i in near:
+        x, y, _, _ = scene.pose_of(int(i), int(i))
+        target = round(x / (width / bins)) * (width / bins)
+        best = np.float32(scene.q_xy[i, 0] + (target - x))
+        cands = [np.nextafter(best, np.float32(-1e9)), best, np.nextafter(best, np.float32(1e9))]
+        errs = []
+        for c in cands:
+            scene.q_xy[i, 0] = c
+            errs.append(abs(scene.pose_of(int(i), int(i))[0] - target))
+        scene.q_xy[i, 0] = cands[int(np.argmin(errs))]
+    return scene, n
+
+
+def test_matches_on_bin_boundaries_are_resolved_bit_exactly():
+    """SURVEY H4.  Poses exactly on (alpha = 0, integer geometry) and within float32 resolution of bin
+    boundaries: the device flags them (counters[2] > 0), confirms the truncation for every admissible
+    libm (counters[4] == 0) and the Hough dict - keys in insertion order, votes, members - is the
+    oracle's (CPython math / glibc) bit for bit."""
+    from sod_b200 import engine as E
+    scene, n = _boundary_scene()
+    sc = E.SceneArrays(scene.q_xy, scene.q_angle, scene.q_octave, scene.m_xy, scene.m_angle, scene.m_octave,
+                       scene.m_image, scene.img_centroid, scene.img_size, np.array([[scene.width, scene.height]], np.int32))
+    ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    res = E.HoughVoter(sc, 15).vote(ids, ids)
+    h = res.host()
+    assert h["n_near_edge"] >= 300 and h["n_unresolved_edge"] == 0
+    flags = res.near_edge[:n].cpu().numpy()
+    assert set(np.unique(flags)) <= {0, 1} and flags.sum() == h["n_near_edge"]
+    table = O.hough_vote(scene, np.arange(n), np.arange(n), 15)
+    np.testing.assert_array_equal(_decode(h["code"], 15), np.array([k[1:] for k in table.keys()]))
+    np.testing.assert_array_equal(h["count"], [b.votes for b in table.values()])
+    for i, b in enumerate(table.values()):
+        np.testing.assert_array_equal(h["members"][h["offset"][i]:h["offset"][i] + h["count"][i]], b.members)
+    # base bins one by one, including x < 0 (int() truncates toward zero) and x = W (votes dropped at the top)
+    want = np.array([O.bin_index(scene.pose_of(i, i), 15, scene.height, scene.width) for i in range(n)])
+    got = res.base_bin[:n].cpu().numpy().astype(np.int64)
+    np.testing.assert_array_equal(np.stack([got & 0xFF, got >> 8 & 0xFF, got >> 16 & 0xFF, got >> 24], 1), want)

@@ -120,3 +120,35 @@ def test_post_process_equals_reference():
     assert [i for sub in flat for i in sub] == z["sub_members"].tolist()
     np.testing.assert_array_equal(np.array(ori, np.float64), z["orientation"])
     np.testing.assert_array_equal(np.array(final, np.float64), z["final"])
+
+
+def test_affine_on_rank_deficient_bins_equals_reference():
+    """tests/golden/affine_singular.npz: the reference's AffineParameters + the fixed-point loop of
+    Main.apply_affine_parameters on bins with duplicate model locations, collinear points, threshold
+    sizes and ill-conditioned normal matrices.  The oracle restates them bit for bit."""
+    z = np.load(GOLD / "affine_singular.npz")
+    off = z["off"]
+    n = len(z["names"])
+    total = int(off[-1])
+    scene = O.Scene(z["query"], np.zeros(total, np.float32), np.zeros(total, np.int32), z["model"],
+                    np.zeros(total, np.float32), np.zeros(total, np.int32), np.zeros(total, np.int32),
+                    np.zeros((1, 2)), np.ones((1, 2)), int(z["width"]), int(z["height"]))
+    ids = np.arange(total)
+    bins = []
+    for b in range(n):
+        mem = list(range(int(off[b]), int(off[b + 1])))
+        fit = O.affine_fit([tuple(float(v) for v in r) for r in z["model"][mem]],
+                           [tuple(float(v) for v in r) for r in z["query"][mem]])
+        np.testing.assert_array_equal(np.asarray(fit), z["first_params"][b])
+        bn = O.Bin(0, (0, 0, 0, int(z["isigma"][b])), (1500, 1000), mem[0], (0.0, 0.0, 0.0, 1.0))
+        bn.members, bn.votes = mem, len(mem)
+        bins.append(bn)
+    live = O.affine_verify(scene, ids, ids, bins, int(z["threshold"]))
+    np.testing.assert_array_equal([any(b is v for v in live) for b in bins], z["live"])
+    np.testing.assert_array_equal([b.votes for b in bins], z["votes"])
+    np.testing.assert_array_equal(np.array([b.affine for b in bins]), z["last_params"])
+    keep = np.zeros(total, bool)
+    for b in bins:
+        keep[b.members] = True
+    np.testing.assert_array_equal(keep, z["keep"])
+    assert 0 < z["live"].sum() < n and 0 < z["keep"].sum() < total

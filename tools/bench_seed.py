@@ -6,6 +6,9 @@ A 1M-row database, 1.28M queries; the "shard" is the first `rows` rows.  Variant
   seeded  thresholds from a sweep of an even 16k-row sample of the WHOLE database (what the ranks hold
           after the min-reduce in DetectionPipeline.detect_device)
   ideal   thresholds = the final global 2nd best (the floor of any threshold-sharing scheme)
+  staged  (with `--staged G`, shards of ndb / G rows) the seeded sweep in two halves with a MIN all-reduce of
+          the thresholds between them, the other G - 1 ranks played by this GPU outside the timed regions:
+          after half of every shard the bound is the best 2nd best any rank has seen in 1/2 of the database
 """
 import sys
 from pathlib import Path
@@ -35,9 +38,36 @@ def timed(f, iters=4):
     return float(np.median(ts))
 
 
+def staged(db, q, seeded, world, nq, stages=2):
+    """Rank 0's shard sweep in `stages` ranges with a min-reduce of all ranks' thresholds between them."""
+    rows = db.shape[0] // world
+    ms = [E.Matcher(E.prepare_db(db[r * rows:(r + 1) * rows].contiguous(), index_base=r * rows)) for r in range(world)]
+    tiles = ms[0].n_tiles
+    cuts = [tiles * k // stages for k in range(stages + 1)]
+    thr = [seeded.clone() for _ in range(world)]
+    total, lists = 0.0, []
+    for k in range(stages):
+        rng = (cuts[k], cuts[k + 1])
+        keep = thr[0].clone()
+        total += timed(lambda: ms[0].top2(q, rng, thr[0].copy_(keep)))
+        lists.append(ms[0].top2(q, rng, thr[0].copy_(keep)))
+        for r in range(1, world):
+            ms[r].top2(q, rng, thr[r])
+        red = torch.stack(thr).min(0).values          # the MIN all-reduce
+        for r in range(world):
+            thr[r].copy_(red)
+    return total, lists, ms[0]
+
+
 def main():
     nq, ndb = 1_280_000, 1_000_000
-    shards = [int(a) for a in sys.argv[1:]] or [125_000, 500_000]
+    argv = sys.argv[1:]
+    world = 0
+    if "--staged" in argv:
+        i = argv.index("--staged")
+        world = int(argv[i + 1])
+        del argv[i:i + 2]
+    shards = [int(a) for a in argv] or [125_000, 500_000]
     g = torch.Generator(device="cuda").manual_seed(3)
     db, q = sift_like_gpu(ndb, g), sift_like_gpu(nq, g)
     full = E.Matcher(E.prepare_db(db))
@@ -50,6 +80,16 @@ def main():
     t_seed_all = timed(lambda: seed_m.top2(q, None, seeded.fill_(0x7F7F7F7F)))
     print(f"seed sweep of ALL {nq} rows on {seed_m.shard.n} sample rows: {t_seed_all:.3f} ms "
           f"(a rank does 1/G of it)", flush=True)
+    if world:
+        for stages in (2, 3, 4):
+            t, lists, m0 = staged(db, q, seeded, world, nq, stages)
+            # exactness: entries within the final global bound survive in the union of the ranges' lists
+            ref_i, ref_d = m0.top2(q)
+            mi, md, _, _ = E.merge_top2(torch.stack([l[0] for l in lists]), torch.stack([l[1] for l in lists]))
+            keep = (ref_d >= 0) & (ref_d - qn[:, None] <= ideal[:nq, None])
+            assert torch.equal(mi[keep], ref_i[keep]) and torch.equal(md[keep], ref_d[keep])
+            print(f"staged x{stages} over {world} ranks, shard {ndb // world} rows: {t:8.3f} ms "
+                  f"(sum of the range sweeps; + {stages - 1} MIN all-reduce(s) of {nq * 4 / 1e6:.1f} MB)", flush=True)
     for rows in shards:
         m = E.Matcher(E.prepare_db(db[:rows].contiguous()))
         ref_i, ref_d = m.top2(q)
