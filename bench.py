@@ -347,7 +347,8 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
         q = {k: v[lo:hi] for k, v in q.items()}
         nq = hi - lo
     pipe = DetectionPipeline(make_database(wl), nq, wl["frame_wh"], rank=rank, world=world, device=device,
-                             shard=shard, exchange=args.exchange, result_rows="own")
+                             shard=shard, exchange=args.exchange, result_rows="own", seed_rows=args.seed_rows,
+                             sweep_stages=args.sweep_stages)
     host = {k: torch.from_numpy(np.ascontiguousarray(q[k])).pin_memory()
             for k in ("q_xy", "q_angle", "q_octave", "q_frame")}
     host["q_des"] = q["q_des"].cpu().pin_memory()
@@ -374,10 +375,14 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
     clocks = sampler.stop() if sampler else None
     stage = {k: _stage_ms(k) for k in _capi.STAGES}
     _capi.timing_enable(False)
-    # a seeded database-sharded step launches the matcher twice: seeding sweep, then the shard sweep
-    per_step = 2 if (pipe.seed_matcher is not None and nq >= pipe.seed_min_queries) else 1
-    sweeps = stage["match"][per_step - 1::per_step]
-    seeds = stage["match"][0::per_step] if per_step == 2 else []
+    # a seeded database-sharded step launches the matcher several times: the seeding sweep, then the shard
+    # sweep in pipe.sweep_stages tile ranges; kernel_ms is the SUM of the shard-sweep launches of a step
+    seeded = pipe.seed_matcher is not None and nq >= pipe.seed_min_queries
+    per_step = 1 + pipe.sweep_stages if seeded else 1
+    mm = stage["match"][: len(stage["match"]) // per_step * per_step]
+    n_steps = max(len(mm) // per_step, 1)
+    sweeps = [sum(mm[i * per_step + (1 if seeded else 0):(i + 1) * per_step]) for i in range(len(mm) // per_step)]
+    seeds = mm[0::per_step] if seeded else []
     loc = torch.tensor([e0.elapsed_time(e1), float(np.mean(sweeps)) if sweeps else 0.0,
                         float(np.mean(seeds)) if seeds else 0.0,
                         float(np.mean(stage["hough_vote"])) if stage["hough_vote"] else 0.0,
@@ -688,7 +693,7 @@ def run_ours(args):
                          "kernel_ms": m["sweep_ms"],
                          "kernel_ms_what": "mean CUDA-event duration of the match_top2_kernel launch alone (sod_timing_*), "
                                            "max over ranks",
-                         "seed_sweep_ms": m["seed_ms"],
+                         "seed_sweep_ms": m["seed_ms"], "sweep_stages": pipe.sweep_stages if m["seed_ms"] else 1,
                          "peak_source": ("max(2 x MEASURED_PEAKS.bf16_tflops_sustained = %.1f, cuBLASLt int8 8192^3 GEMM "
                                          "measured in this run = %.1f); MEASURED_PEAKS.json has no int8 entry%s"
                                          % (2.0 * bf16_sus, int8_tops or 0.0, "" if peaks else " (file absent: 1400 fallback)")),
@@ -778,6 +783,10 @@ def main():
     ap.add_argument("--shard", default="db", choices=["db", "frames"],
                     help="N > 1: split the database rows (default: the north star's layout, one exchange of the "
                          "shard-local top-2) or the frames (database replicated, no collective)")
+    ap.add_argument("--seed-rows", type=int, default=None,
+                    help="--shard db: rows of the replicated threshold-seeding sample (0 = off; default: pipeline's)")
+    ap.add_argument("--sweep-stages", type=int, default=None,
+                    help="--shard db with seeding: tile ranges of the shard sweep with a threshold all-reduce between them")
     ap.add_argument("--no-alt", action="store_true", help="N > 1: skip the sub-record of the other partition")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5 sub-records")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle spot check")

@@ -31,7 +31,9 @@ def shard_bounds(n_objects: int, rows_per_object: np.ndarray | int, rank: int, w
     return obj_lo, obj_hi, int(starts[obj_lo]), int(starts[obj_hi])
 
 
-SEED_ROWS = 16384          # size of the threshold-seeding sample of a sharded database
+SEED_ROWS = 16384          # size of the threshold-seeding sample of a database sharded over 8 ranks
+SEED_ROWS_PER_RANK = 2048  # default sample size = this x world: a rank seeds 1/world of the query rows, so the
+                           # seeding sweep costs every rank the same ~0.45 ms per 1.28 M query rows
 SEED_MIN_DB_ROWS = 262144  # smaller databases are not seeded by default: the sweep is short anyway
 SEED_MIN_QUERIES = 65536   # smaller batches skip the seeding sweep: a launch and an all-reduce cost more
 QUERY_BLOCK = 256          # query rows per matcher unit: threshold slices must start on this boundary
@@ -91,7 +93,8 @@ class DetectionPipeline:
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
                  affine_threshold: int = 4, per_object_spaces: bool | None = None,
                  device: str | torch.device = "cuda", shard: str = "db", seed_rows: int | None = None,
-                 exchange: str = "scatter", replicated_host: bool = True, result_rows: str = "all"):
+                 exchange: str = "scatter", replicated_host: bool = True, result_rows: str = "all",
+                 sweep_stages: int | None = None):
         """Hough spaces.  The reference votes ALL model images into one dict (main.py:30,113-119: the
         database is several training views of one object), and that is the default here: one space
         per frame.  A multi-object database names the object of every model image in
@@ -105,8 +108,12 @@ class DetectionPipeline:
         gives each rank its own frames (no collective at all); the pipeline then behaves exactly like a
         single-GPU one.
         seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
-        seeds the pruning thresholds (see detect_device); 0 = off; None = SEED_ROWS when the database has
-        at least SEED_MIN_DB_ROWS rows.  Batches below SEED_MIN_QUERIES rows skip the seeding sweep.
+        seeds the pruning thresholds (see detect_device); 0 = off; None = SEED_ROWS_PER_RANK x world when the
+        database has at least SEED_MIN_DB_ROWS rows.  Batches below SEED_MIN_QUERIES rows skip the seeding sweep.
+        sweep_stages (seeded runs only): the shard sweep runs in this many tile ranges with a MIN all-reduce
+        of the thresholds between them - after half of every shard the bound is the best 2nd best any rank
+        has seen in half of the WHOLE database (B200, 8 x 125k rows: 14.5 ms in two stages against 15.7 ms
+        in one, profiles/r02_seed_staged.txt); None = 2.
         replicated_host (shard="db", several ranks): every rank is handed the same HOST batch, so each
         uploads only its 1/G slice of the rows over its own PCIe link and one all-gather over NVLink
         replicates it on the devices (load_queries); False = every rank uploads the whole batch.
@@ -124,6 +131,7 @@ class DetectionPipeline:
         self.exchange = exchange
         self.replicated_host, self.result_rows = bool(replicated_host), result_rows
         self.seed_min_queries = SEED_MIN_QUERIES
+        self.sweep_stages = 2 if sweep_stages is None else max(1, int(sweep_stages))
         self.shard_mode = shard
         if shard == "frames":
             rank, world = 0, 1
@@ -168,7 +176,7 @@ class DetectionPipeline:
             # seeds pruning thresholds (detect_device).  The choice depends on the whole database and on
             # the argument alone, so it is the same on every rank.
             if seed_rows is None:
-                seed_rows = SEED_ROWS if len(image) >= SEED_MIN_DB_ROWS else 0
+                seed_rows = SEED_ROWS_PER_RANK * world if len(image) >= SEED_MIN_DB_ROWS else 0
             if world > 1 and seed_rows > 0:
                 rows = seed_sample_rows(len(image), seed_rows)
                 sample = db.des[torch.from_numpy(rows)] if isinstance(db.des, torch.Tensor) else \
@@ -212,7 +220,7 @@ class DetectionPipeline:
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
         self.launches_per_call = 16 + (2 if world > 1 and not self.float_path and exchange == "scatter" else 0) + \
-            (3 if self.seed_matcher is not None else 0)
+            (3 + (3 if self.sweep_stages > 1 else 0) if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
     def _qset(self, slot: int) -> dict:
@@ -294,7 +302,22 @@ class DetectionPipeline:
             if s_hi > s_lo:
                 self.seed_matcher.top2(q[s_lo:s_hi], None, thr[s_lo:])
             dist.all_reduce(thr, op=dist.ReduceOp.MIN, group=self.group)
-            idx, d2 = self.matcher.top2(q, None, thr)
+            # The shard sweep in stages: between two tile ranges the ranks min-reduce their thresholds again.
+            # Every rank's value is the 2nd best of rows it has really seen (or the seed's), so the minimum is
+            # still an upper bound of the final 2nd best; after the first half of every shard it is nearly the
+            # final one, and the second half runs almost without top-2 updates.
+            tiles = self.matcher.n_tiles
+            stages = min(self.sweep_stages, max(tiles, 1))
+            cuts = [tiles * k // stages for k in range(stages + 1)]
+            parts = []
+            for k in range(stages):
+                parts.append(self.matcher.top2(q, (cuts[k], cuts[k + 1]), thr, prepared=k > 0))
+                if k + 1 < stages:
+                    dist.all_reduce(thr, op=dist.ReduceOp.MIN, group=self.group)
+            if stages == 1:
+                idx, d2 = parts[0]
+            else:
+                idx, d2, _, _ = E.merge_top2(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
         else:
             idx, d2 = self.matcher.top2(q)
         if self.world > 1 and not self.float_path and self.exchange == "scatter":

@@ -52,7 +52,12 @@ def main():
     seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024)
     seeded_pipe.seed_min_queries = 0
     assert seeded_pipe.seed_matcher is not None
+    assert seeded_pipe.sweep_stages == 2                     # the shard sweep in two ranges + a mid all-reduce
     seeded = seeded_pipe.detect(*q)
+    one_stage = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024,
+                                  sweep_stages=1)
+    one_stage.seed_min_queries = 0
+    same(sharded, one_stage.detect(*q), "one-stage seeded sweep")
     # and with the gather form of the exchange (all-gather of the lists + merge on every rank)
     gathered_lists = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,
                                        exchange="gather").detect(*q)
