@@ -418,34 +418,44 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
                 launches=pipe.launches_per_call)
 
 
-def latency_record(pipe, n, world, device, barrier, iters=20):
+def latency_record(pipe, n, world, device, barrier, iters=30):
     """BASELINE configs[2]: one small query batch (n rows) against the sharded 1M database - latency of
-    the whole path per call (median, max over ranks) + the matcher's share."""
+    the whole path per call (median, max over ranks): eager (one launch per kernel) and as one CUDA-graph
+    replay (DetectionPipeline.detect_replay), + the matcher kernel's own duration."""
     import torch
     import torch.distributed as dist
     from sod_b200 import _capi
+
+    def timed(fn):
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            a.record()
+            fn(n)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
     for _ in range(3):
         pipe.detect_device(n)
     barrier()
     _capi.timing_enable(True)
-    ts = []
-    for _ in range(iters):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
-        a.record()
-        pipe.detect_device(n)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+    eager = timed(pipe.detect_device)
     m = _stage_ms("match")
     for k in _capi.STAGES:
         _stage_ms(k)
-    _capi.timing_enable(False)
-    loc = torch.tensor([float(np.median(ts)), float(np.median(m))], device=device, dtype=torch.float64)
+    _capi.timing_enable(False)       # event records must not be captured into the graph
+    barrier()
+    pipe.detect_replay(n)            # first call captures
+    barrier()
+    graph = timed(pipe.detect_replay)
+    loc = torch.tensor([eager, graph, float(np.median(m))], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(loc, op=dist.ReduceOp.MAX)
-    return float(loc[0]), float(loc[1])
+    return float(loc[0]), float(loc[1]), float(loc[2])
 
 
 def oracle_spot_check(wl, res, pipe, args, rows=64):
@@ -606,8 +616,7 @@ def run_ours(args):
     # ---------------- BASELINE configs[2]: 10k-query latency against the (sharded) 1M database
     c3 = None
     if not args.no_configs and nq >= 10_000:
-        lat_ms, lat_match_ms = latency_record(pipe, 10_000, world, device, barrier)
-        c3 = (lat_ms, lat_match_ms)
+        c3 = latency_record(pipe, 10_000, world, device, barrier)
 
     # ---------------- the other partition of the same work, for the record (N > 1 only)
     alt = None
@@ -618,7 +627,7 @@ def run_ours(args):
             del host_keep
             a = measure(args, wl, other, rank, world, local, device, barrier, with_clocks=False)
             alt = {"parallelism": (f"frame-shard{world}, database replicated, no collective" if other == "frames"
-                                   else f"db-shard{world}+{args.exchange}-top2"),
+                                   else f"db-shard{world}"),
                    "value": a["nq_total"] * args.steps / (a["ms_total"] * 1e-3), "ms_per_step": a["ms_total"] / args.steps,
                    "kernel_ms": a["sweep_ms"], "e2e": {"value": a["nq_total"] * args.steps / a["e2e_s"], "unit": UNIT,
                                                        "h2d_bytes_per_step": a["h2d"], "d2h_bytes_per_step": a["d2h"]}}
@@ -670,7 +679,8 @@ def run_ours(args):
         achieved = ops / (m["sweep_ms"] * 1e-3) / 1e12
         par = ("single" if world == 1 else
                f"db-shard{world}: database rows split at object boundaries, query batch replicated (1/{world} uploaded per "
-               f"rank + NVLink all-gather), NCCL {args.exchange} exchange of the shard-local top-2, Hough+affine by object"
+               f"rank + NVLink all-gather), NCCL {'scatter' if args.exchange in ('auto', 'peer') else args.exchange} exchange of the "
+               f"shard-local top-2, Hough+affine by object"
                if args.shard == "db" else f"frame-shard{world}, database replicated, no collective")
         line = {
             "metric": METRIC, "value": nq_total * args.steps / (m["ms_total"] * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -710,11 +720,15 @@ def run_ours(args):
             line["parity"] = check
         configs = {}
         if c3 is not None:
-            ach3 = 2.0 * 10_000 * shard_rows * 128 / (c3[1] * 1e-3) / 1e12
+            ach3 = 2.0 * 10_000 * shard_rows * 128 / (c3[2] * 1e-3) / 1e12
+            xchg = ("none" if world == 1 else "peer memory (sod_top2_exchange_peer: 2 kernels, no collective call)"
+                    if pipe.peer is not None else f"NCCL scatter (peer memory unavailable: {pipe.peer_error})")
             configs["C3"] = {"workload": f"10,000-descriptor query vs the 1M-descriptor database on {world} GPU(s) "
-                                         "(BASELINE configs[2]), whole path per call",
-                             "ms": c3[0], "kernel_ms": c3[1], "achieved": ach3, "unit": "TFLOP/s", "frac": ach3 / peak,
-                             "exchange": "none" if world == 1 else f"NCCL {args.exchange}"}
+                                         "(BASELINE configs[2]), whole path per call (2-NN + ratio + Hough + affine)",
+                             "ms": c3[1], "ms_what": "one CUDA-graph replay of the path (DetectionPipeline.detect_replay), "
+                                                     "median of 30, max over ranks",
+                             "ms_eager": c3[0], "kernel_ms": c3[2], "achieved": ach3, "unit": "TFLOP/s",
+                             "frac": ach3 / peak, "exchange": xchg}
         if world == 1 and not args.no_configs:
             try:
                 configs.update(config_records(device, peak, hbm))
@@ -790,7 +804,7 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="N > 1: skip the sub-record of the other partition")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5 sub-records")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle spot check")
-    ap.add_argument("--exchange", default="scatter", choices=["scatter", "gather"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "scatter", "gather"],
                     help="--shard db: how the shard-local top-2 are merged (DetectionPipeline)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

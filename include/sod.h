@@ -139,6 +139,31 @@ int sod_top2_merge_keys(const int64_t* parts, int32_t n_parts, int64_t n_rows, i
 int sod_top2_from_keys(const int64_t* keys, int64_t n_query, int32_t* out_idx, uint32_t* out_d2, float* out_dist,
                        uint8_t* out_pass, double ratio, sod_stream_t stream);
 
+/* K3 over peer memory: the same merge for query batches small enough that two NCCL calls would cost more
+ * than the matching itself (BASELINE configs[2]: 10k query descriptors against a 1M-row database on 8 GPUs).
+ * Every rank owns one exchange buffer of sod_exchange_bytes(max_query, world) bytes, allocated by
+ * sod_exchange_alloc (cudaMalloc memory, zeroed; the one place this library allocates: IPC export needs a
+ * whole allocation), exported with sod_ipc_export (a 64-byte cudaIpcMemHandle_t the caller passes to the
+ * other processes of the node by any means) and mapped by every peer with sod_ipc_open.
+ * sod_top2_exchange_peer(idx, d2, ...) stores this rank's lists as packed keys into slot `rank` of EVERY
+ * rank's buffer (peer stores over NVLink), publishes a call counter there, waits until the counters of all
+ * ranks have arrived in its own buffer, merges the G candidates per row and writes out_idx / out_d2 /
+ * out_dist / out_pass exactly as sod_top2_merge does - two kernels on the caller's stream, no host
+ * synchronisation, capturable in a CUDA graph (the call counter lives in the buffer).  Every rank must make
+ * the same sequence of calls; peer_buffers_host is a HOST array of `world` device pointers (entry `rank` =
+ * the own buffer).  A rank that waits ~4 s for a peer traps (launch error) instead of hanging. */
+#define SOD_EXCHANGE_MAX_RANKS 16
+#define SOD_IPC_HANDLE_BYTES 64
+size_t sod_exchange_bytes(int64_t max_query, int32_t world);
+int sod_exchange_alloc(size_t bytes, void** buffer_out);
+int sod_exchange_free(void* buffer);
+int sod_ipc_export(const void* buffer, uint8_t* handle_host);
+int sod_ipc_open(const uint8_t* handle_host, void** buffer_out);
+int sod_ipc_close(void* buffer);
+int sod_top2_exchange_peer(const int32_t* idx, const uint32_t* d2, int64_t n_query, int32_t rank, int32_t world,
+                           void* const* peer_buffers_host, int64_t max_query, int32_t* out_idx, uint32_t* out_d2,
+                           float* out_dist, uint8_t* out_pass, double ratio, sod_stream_t stream);
+
 /* ---- bf16 fallback for descriptors that are NOT integer-valued 0..255 (non-OpenCV extractors,
  * normalised float descriptors).  Same reference call as sod_match_top2 (main.py:70-73), approximate
  * distances: d^2 = |q|^2 + |t|^2 - 2 q.t with fp32 norms and the dot product on tcgen05 kind::f16

@@ -31,6 +31,7 @@
 #include "sod_common.cuh"
 #include "sod_ptx.cuh"
 #include "sod_tma.cuh"
+#include "sod_top2.cuh"
 
 namespace sod {
 namespace {
@@ -508,26 +509,6 @@ __global__ void pack_u8_kernel(const float4* __restrict__ src, int64_t n_vec4,
   if (bad) atomicOr(nonint_flag, 1);
 }
 
-// Output of one merged row + the ratio test exactly as the reference evaluates it (main.py:81-82).
-__device__ __forceinline__ void write_top2_row(int64_t row, int32_t i1, uint32_t d1, int32_t i2, uint32_t d2,
-                                               int32_t* __restrict__ out_idx, uint32_t* __restrict__ out_d2,
-                                               float* __restrict__ out_dist, uint8_t* __restrict__ out_pass,
-                                               double ratio) {
-  out_idx[row * 2 + 0] = i1;
-  out_idx[row * 2 + 1] = i2;
-  out_d2[row * 2 + 0] = d1;
-  out_d2[row * 2 + 1] = d2;
-  // OpenCV reports sqrt of the float32 squared distance; d2 < 2^24 converts exactly.
-  const float f1 = (i1 >= 0) ? __fsqrt_rn(static_cast<float>(d1)) : __int_as_float(0x7f800000);
-  const float f2 = (i2 >= 0) ? __fsqrt_rn(static_cast<float>(d2)) : __int_as_float(0x7f800000);
-  if (out_dist) {
-    out_dist[row * 2 + 0] = f1;
-    out_dist[row * 2 + 1] = f2;
-  }
-  if (out_pass)
-    out_pass[row] = (i2 >= 0 && static_cast<double>(f1) < ratio * static_cast<double>(f2)) ? 1 : 0;
-}
-
 // K3: merge candidate lists, exact ratio test.
 __global__ void top2_merge_kernel(const int32_t* __restrict__ parts_idx,
                                   const uint32_t* __restrict__ parts_d2, int n_parts, int64_t nq,
@@ -563,8 +544,6 @@ __global__ void top2_merge_kernel(const int32_t* __restrict__ parts_idx,
 // K3, exchange form.  A candidate as one signed 64-bit key (d2 << 32 | global row): signed order is the
 // (distance, index) order of the merge.  No entry: kNoneKey.  Keys travel as [row][2] pairs, so a
 // contiguous range of query rows is a contiguous message.
-constexpr long long kNoneKey = 0x7FFFFFFFFFFFFFFFll;
-
 __global__ void top2_keys_kernel(const int32_t* __restrict__ idx, const uint32_t* __restrict__ d2, int64_t nq,
                                  int64_t n_rows, longlong2* __restrict__ keys) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;

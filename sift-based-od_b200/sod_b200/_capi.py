@@ -96,6 +96,13 @@ _PROTOS = {
     "sod_top2_keys": (C.c_int, [_p, _p, _i64, _i64, _p, _p]),
     "sod_top2_merge_keys": (C.c_int, [_p, _i32, _i64, _p, _p]),
     "sod_top2_from_keys": (C.c_int, [_p, _i64, _p, _p, _p, _p, C.c_double, _p]),
+    "sod_exchange_bytes": (C.c_size_t, [_i64, _i32]),
+    "sod_exchange_alloc": (C.c_int, [C.c_size_t, C.POINTER(_p)]),
+    "sod_exchange_free": (C.c_int, [_p]),
+    "sod_ipc_export": (C.c_int, [_p, _p]),
+    "sod_ipc_open": (C.c_int, [_p, C.POINTER(_p)]),
+    "sod_ipc_close": (C.c_int, [_p]),
+    "sod_top2_exchange_peer": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _p, C.c_double, _p]),
     "sod_bf16_operand_cols": (_i64, [_i32]),
     "sod_bf16_db_rows": (_i64, [_i64]),
     "sod_bf16_prepare": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p]),

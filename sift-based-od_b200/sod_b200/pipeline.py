@@ -36,6 +36,7 @@ SEED_ROWS_PER_RANK = 2048  # default sample size = this x world: a rank seeds 1/
                            # seeding sweep costs every rank the same ~0.45 ms per 1.28 M query rows
 SEED_MIN_DB_ROWS = 262144  # smaller databases are not seeded by default: the sweep is short anyway
 SEED_MIN_QUERIES = 65536   # smaller batches skip the seeding sweep: a launch and an all-reduce cost more
+PEER_MAX_QUERIES = 65536   # largest batch whose shard merge goes through peer memory (exchange="auto" / "peer")
 QUERY_BLOCK = 256          # query rows per matcher unit: threshold slices must start on this boundary
 
 
@@ -93,7 +94,7 @@ class DetectionPipeline:
                  world: int = 1, group=None, bins: int = 15, vote_threshold: int = 5,
                  affine_threshold: int = 4, per_object_spaces: bool | None = None,
                  device: str | torch.device = "cuda", shard: str = "db", seed_rows: int | None = None,
-                 exchange: str = "scatter", replicated_host: bool = True, result_rows: str = "all",
+                 exchange: str = "auto", replicated_host: bool = True, result_rows: str = "all",
                  sweep_stages: int | None = None):
         """Hough spaces.  The reference votes ALL model images into one dict (main.py:30,113-119: the
         database is several training views of one object), and that is the default here: one space
@@ -121,11 +122,16 @@ class DetectionPipeline:
         row on every rank; "own" = only the rows of the rank's slice (out["row_lo"] is the first), which
         is all a caller that collects the ranks' answers needs.
         exchange (shard="db"): "scatter" = all-to-all of packed keys, slice merge, all-gather of the merged
-        slices; "gather" = all-gather of every rank's lists + sod_top2_merge on every rank."""
+        slices (NCCL); "gather" = all-gather of every rank's lists + sod_top2_merge on every rank (NCCL);
+        "peer" = packed keys stored straight into every rank's exchange buffer over NVLink + a flag barrier,
+        two kernels and no collective call (sod_b200/peer.py; batches up to PEER_MAX_QUERIES rows);
+        "auto" (default) = peer for batches up to PEER_MAX_QUERIES rows, scatter above (G x 16 B per row
+        and rank against 2 x 16 B) - and scatter throughout if the node cannot map peer memory
+        (self.peer_error says why)."""
         if shard not in ("db", "frames"):
             raise ValueError("shard must be 'db' or 'frames'")
-        if exchange not in ("scatter", "gather"):
-            raise ValueError("exchange must be 'scatter' or 'gather'")
+        if exchange not in ("scatter", "gather", "peer", "auto"):
+            raise ValueError("exchange must be 'auto', 'peer', 'scatter' or 'gather'")
         if result_rows not in ("all", "own"):
             raise ValueError("result_rows must be 'all' or 'own'")
         self.exchange = exchange
@@ -212,6 +218,16 @@ class DetectionPipeline:
         self._copy_stream = None
         self._loaded = [None, None]      # event: the set's host->device copies have landed
         self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
+        self.peer, self.peer_error = None, None
+        if world > 1 and not self.float_path and self.exchange in ("peer", "auto"):
+            from .peer import PeerExchange
+            try:
+                self.peer = PeerExchange(min(self.max_queries, PEER_MAX_QUERIES), rank, world, group, dev)
+            except Exception as exc:      # e.g. a container that forbids CUDA IPC between its processes
+                if self.exchange == "peer":
+                    raise
+                self.peer_error = repr(exc)
+        self._graphs: dict = {}
         if world > 1 and (self.float_path or self.exchange == "gather"):
             self._gather_idx = torch.empty((world, self.max_queries, 2), dtype=torch.int32, device=dev)
             self._gather_d2 = torch.empty((world, self.max_queries, 2),
@@ -219,7 +235,7 @@ class DetectionPipeline:
         # our kernels per detect_device call; the key exchange of a database-sharded run is
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
-        self.launches_per_call = 16 + (2 if world > 1 and not self.float_path and exchange == "scatter" else 0) + \
+        self.launches_per_call = 16 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
             (3 + (3 if self.sweep_stages > 1 else 0) if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
@@ -277,10 +293,40 @@ class DetectionPipeline:
             self._loaded[slot] = None
         return n
 
-    def detect_device(self, n: int, slot: int = 0):
+    def detect_replay(self, n: int, slot: int = 0):
+        """detect_device(n, slot) as ONE CUDA-graph launch: the ~20 kernels of a small batch are launch-bound
+        (BASELINE configs[2]: 10k query rows), so the first call with a given (n, slot) runs the path a few
+        times, captures it, and every later call replays the graph.  The result tensors are the graph's own
+        and are overwritten by the next replay.  All ranks of a database-sharded run must call it alike.
+        Batches that would use an NCCL exchange or threshold seeding are not captured (they are not
+        launch-bound): they fall through to detect_device."""
+        uses_nccl = self.world > 1 and not (self.peer is not None and n <= self.peer.max_query)
+        if uses_nccl or n == 0:
+            return self.detect_device(n, slot)
+        cur = torch.cuda.current_stream(self.device)
+        if self._loaded[slot] is not None:
+            cur.wait_event(self._loaded[slot])
+        entry = self._graphs.get((n, slot))
+        if entry is None:
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self.detect_device(n, slot, _events=False)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                result = self.detect_device(n, slot, _events=False)
+            entry = self._graphs[(n, slot)] = (graph, result)
+        entry[0].replay()
+        self._consumed[slot] = torch.cuda.Event()
+        self._consumed[slot].record()
+        return entry[1]
+
+    def detect_device(self, n: int, slot: int = 0, _events: bool = True):
         """Run the path on the first n rows of query-buffer set `slot`; everything stays on the device."""
         qs = self._qset(slot)
-        if self._loaded[slot] is not None:
+        if _events and self._loaded[slot] is not None:
             torch.cuda.current_stream(self.device).wait_event(self._loaded[slot])
         sc = self.scene
         self.q_des, sc.q_xy, sc.q_angle, sc.q_octave, sc.q_frame = (qs["des"], qs["xy"], qs["angle"], qs["octave"],
@@ -320,7 +366,10 @@ class DetectionPipeline:
                 idx, d2, _, _ = E.merge_top2(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
         else:
             idx, d2 = self.matcher.top2(q)
-        if self.world > 1 and not self.float_path and self.exchange == "scatter":
+        if self.world > 1 and self.peer is not None and n <= self.peer.max_query:
+            # The exchange through peer memory: two kernels, no collective call (sod_b200/peer.py).
+            idx, d2, dist_f, ok = self.peer.merge(idx, d2)
+        elif self.world > 1 and not self.float_path and self.exchange != "gather":
             # The exchange in scatter form: candidates travel as signed 64-bit keys
             # (d2 << 32 | global row), rank r merges the query rows of slice r from all ranks
             # (all-to-all), the merged slices are gathered: 2 x 16 B per query row instead of G x 16 B.
@@ -345,8 +394,9 @@ class DetectionPipeline:
         hough = self.voter.vote(mq, mt, n_dev, detail_min_count=self.vote_threshold)
         aff = E.affine_verify(self.scene, mq, mt, hough, self.vote_threshold, self.affine_threshold,
                               result=self._aff)
-        self._consumed[slot] = torch.cuda.Event()
-        self._consumed[slot].record()
+        if _events:
+            self._consumed[slot] = torch.cuda.Event()
+            self._consumed[slot].record()
         return dict(idx=idx, d2=d2, dist=dist_f, ok=ok, match_q=mq, match_t=mt, n_matches=n_dev,
                     hough=hough, affine=aff, n=n)
 

@@ -42,7 +42,15 @@ def main():
     # host batch: every rank uploads its slice of the rows, an all-gather replicates it (load_queries)
     pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev)
     assert pipe.seed_matcher is None and pipe.spaces_per_frame == args.objects
-    sharded = pipe.detect(*q)
+    assert pipe.peer is not None, f"peer-memory exchange unavailable: {pipe.peer_error}"
+    sharded = pipe.detect(*q)                                 # 9000 rows: the exchange goes through peer memory
+    same(sharded, DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,
+                                    exchange="scatter").detect(*q), "the NCCL scatter exchange")
+    # the whole path as one CUDA-graph replay (latency configuration), twice, and eager again after it
+    pipe.load_queries(*q)
+    for _ in range(2):
+        same(sharded, pipe.fetch(pipe.detect_replay(nq)), "the CUDA-graph replay")
+    same(sharded, pipe.detect(*q), "eager after graph")
     # device-resident batch (no slicing), and a host batch uploaded whole by every rank
     same(sharded, pipe.detect(*q_dev), "device-resident inputs")
     same(sharded, DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,

@@ -201,3 +201,39 @@ def test_key_exchange_equals_list_merge():
     copy = lambda out, inp: out.copy_(inp)  # noqa: E731
     for got, ref in zip(E.exchange_merge_top2(i1, d1, 1, copy, copy), E.merge_top2(i1[None], d1[None])):
         assert torch.equal(got, ref)
+
+
+def test_peer_exchange_kernels_with_one_rank():
+    """sod_top2_exchange_peer with world = 1 (the own buffer is the only peer): the push / flag / merge
+    kernels run for real and must reproduce sod_top2_merge of the same single list, call after call (the
+    key slots alternate with the call parity); the multi-rank form is tests/dist_check.py."""
+    import ctypes as C
+    from sod_b200 import engine as E
+    from sod_b200._capi import check, lib
+    rng = np.random.default_rng(31)
+    db = torch.from_numpy(sift_like(rng, 3000)).cuda()
+    matcher = E.Matcher(E.prepare_db(db, index_base=500))
+    cap = 700
+    buf = C.c_void_p()
+    check(lib.sod_exchange_alloc(int(lib.sod_exchange_bytes(cap, 1)), C.byref(buf)), "sod_exchange_alloc")
+    table = (C.c_void_p * 1)(buf.value)
+    try:
+        for call, nq in enumerate((700, 1, 333, 700)):
+            q = torch.from_numpy(sift_like(rng, nq)).cuda()
+            if nq > 10:
+                q[:10] = db[100:110]
+            idx, d2 = matcher.top2(q)
+            want = E.merge_top2(idx[None], d2[None])
+            oi = torch.empty_like(idx); od = torch.empty_like(d2)
+            of = torch.empty((nq, 2), dtype=torch.float32, device="cuda"); ok = torch.empty(nq, dtype=torch.uint8, device="cuda")
+            check(lib.sod_top2_exchange_peer(E._ptr(idx), E._ptr(d2), nq, 0, 1, C.cast(table, C.c_void_p), cap,
+                                             E._ptr(oi), E._ptr(od), E._ptr(of), E._ptr(ok), 0.75, E._stream()),
+                  "sod_top2_exchange_peer")
+            for g, w in zip((oi, od, of, ok), want):
+                assert torch.equal(g, w), f"call {call}"
+        rc = lib.sod_top2_exchange_peer(E._ptr(idx), E._ptr(d2), cap + 1, 0, 1, C.cast(table, C.c_void_p), cap,
+                                        E._ptr(oi), E._ptr(od), None, None, 0.75, E._stream())
+        assert rc == -1 and b"capacity" in lib.sod_last_error()
+    finally:
+        torch.cuda.synchronize()
+        check(lib.sod_exchange_free(buf), "sod_exchange_free")

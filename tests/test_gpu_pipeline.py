@@ -144,3 +144,31 @@ def test_affine_result_of_a_smaller_hough_result_is_refused():
                                 C.byref(o), E._stream()), "sod_affine_verify")
     torch.cuda.synchronize()
     assert int(small_a.counters[1]) == 1 and int(guard.min()) == 7
+
+
+def test_graph_replay_equals_eager_detect():
+    """detect_replay captures the path for a fixed batch size into one CUDA graph; replays return what the
+    eager path returns, also after the query buffers were refilled with another batch."""
+    import torch
+    import bench
+    from sod_b200.pipeline import DetectionPipeline
+    args = type("A", (), dict(objects=40, kp_per_object=400, frames=4, per_frame=1200, instances=3,
+                              inlier_frac=0.2, false_frac=0.02))()
+    dev = torch.device("cuda")
+    wl = bench.make_workload(args, dev)
+    nq = args.frames * args.per_frame
+    pipe = DetectionPipeline(bench.make_database(wl), nq, wl["frame_wh"], device=dev)
+    a = tuple(torch.as_tensor(wl[k]).cpu() for k in ("q_des", "q_xy", "q_angle", "q_octave", "q_frame"))
+    perm = torch.arange(nq).view(args.frames, -1).roll(91, 1).reshape(-1)
+    b = tuple(t[perm].contiguous() if i < 4 else t for i, t in enumerate(a))
+    want_a, want_b = pipe.detect(*a), pipe.detect(*b)
+    assert not np.array_equal(want_a["idx"], want_b["idx"])
+    for batch, want in ((a, want_a), (b, want_b), (a, want_a)):
+        pipe.load_queries(*batch)
+        got = pipe.fetch(pipe.detect_replay(nq))
+        np.testing.assert_array_equal(got["idx"], want["idx"])
+        np.testing.assert_array_equal(got["ok"], want["ok"])
+        og, ow = (np.lexsort((x["valid_code"], x["valid_group"])) for x in (got, want))
+        for k in ("valid_group", "valid_code", "votes", "status", "params"):
+            np.testing.assert_array_equal(got[k][og], want[k][ow])
+    assert len(pipe._graphs) == 1
