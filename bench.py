@@ -444,9 +444,8 @@ def latency_record(pipe, n, world, device, barrier, iters=30):
     barrier()
     _capi.timing_enable(True)
     eager = timed(pipe.detect_device)
-    m = _stage_ms("match")
-    for k in _capi.STAGES:
-        _stage_ms(k)
+    stages = {k: _stage_ms(k) for k in _capi.STAGES}
+    m = stages["match"]
     _capi.timing_enable(False)       # event records must not be captured into the graph
     barrier()
     pipe.detect_replay(n)            # first call captures
@@ -455,7 +454,7 @@ def latency_record(pipe, n, world, device, barrier, iters=30):
     loc = torch.tensor([eager, graph, float(np.median(m))], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(loc, op=dist.ReduceOp.MAX)
-    return float(loc[0]), float(loc[1]), float(loc[2])
+    return float(loc[0]), float(loc[1]), float(loc[2]), {k: float(np.median(v)) for k, v in stages.items() if v}
 
 
 def oracle_spot_check(wl, res, pipe, args, rows=64):
@@ -728,7 +727,7 @@ def run_ours(args):
                              "ms": c3[1], "ms_what": "one CUDA-graph replay of the path (DetectionPipeline.detect_replay), "
                                                      "median of 30, max over ranks",
                              "ms_eager": c3[0], "kernel_ms": c3[2], "achieved": ach3, "unit": "TFLOP/s",
-                             "frac": ach3 / peak, "exchange": xchg}
+                             "frac": ach3 / peak, "exchange": xchg, "stages_ms_rank0": c3[3]}
         if world == 1 and not args.no_configs:
             try:
                 configs.update(config_records(device, peak, hbm))

@@ -88,6 +88,7 @@ struct PoseArgs {
   int32_t* counters;
   int32_t* group_of;
   int32_t* group_count;
+  double* match_size;  // [M][2] (w, h) of the match's model image, or nullptr: read again by the finish kernels
 };
 
 __device__ __forceinline__ int64_t live_count(const int32_t* n_dev, int64_t cap) {
@@ -124,6 +125,8 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
     const XyBins c = xy_bins(ca, sa, tx, ty, qx, qy, bx, by, W, H);
     double* po = a.pose + i * 4;
     po[0] = c.x; po[1] = c.y; po[2] = al; po[3] = s;
+    if (a.match_size)
+      reinterpret_cast<double2*>(a.match_size)[i] = reinterpret_cast<const double2*>(a.sc.image_size)[img];
 
     // theta and sigma bins depend on exact IEEE operations only (no libm): always bit-identical
     const double ft = fmod(__ddiv_rn(__dmul_rn(al, static_cast<double>(bins.t)), kTwoPi),
@@ -270,7 +273,7 @@ struct VoteArgs {
   const int32_t* group_off;  // [n_groups+1]
   const int32_t* grouped;    // match ids grouped by Hough space
   const uint32_t* base_bin;  // base bins in the same (grouped) order
-  uint16_t* creator;         // per grouped position: which of the 16 votes created its bin
+  uint32_t* rank;            // per grouped position 16 slots: arrival rank of each of its votes in its bin
   int64_t n_groups;
   Bins4 bins;
   int group_chunk;           // Hough spaces per ticket: 1 for few large spaces ... kGroupChunk for many sparse ones
@@ -296,12 +299,89 @@ __device__ __forceinline__ void for_each_vote(uint32_t base, const Bins4& bins, 
   }
 }
 
+// One Hough space: the four phases over the matches [beg, end) of the space.  Rank is the element type
+// of the per-vote arrival ranks (uint16_t while the space has at most 65,535 matches: half the traffic).
+//  A  every vote takes the next rank of its bin: ONE shared-memory atomic per vote; rank 0 created the bin
+//  B  the creating vote emits the bin record and turns the counter into the bin's offset
+//  C  every vote stores its match id at offset + rank: no atomic, the ranks of phase A are a permutation
+//  D  creators clear their counters for the next space
+template <typename Rank>
+__device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, int64_t g, int beg, int end,
+                                           int* s_counts) {
+  // s_counts: [0] n_bins, [1] n_votes, [2] rec_base, [3] vote_base, [4] rec_cur, [5] vote_cur, [6] ok
+  const Bins4 bins = a.bins;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_counts[0] = s_counts[1] = s_counts[4] = s_counts[5] = 0;
+  __syncthreads();
+  int my_bins = 0, my_votes = 0;
+  for (int p = beg + tid; p < end; p += kVoteThreads) {
+    Rank* rk = reinterpret_cast<Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+    for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
+      const uint32_t r = atomicAdd(&hist[code], 1u);
+      rk[o] = static_cast<Rank>(r);
+      my_bins += r == 0u;
+      ++my_votes;
+    });
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    my_bins += __shfl_xor_sync(0xffffffffu, my_bins, o);
+    my_votes += __shfl_xor_sync(0xffffffffu, my_votes, o);
+  }
+  if (lane == 0 && my_votes) {
+    atomicAdd(&s_counts[0], my_bins);
+    atomicAdd(&s_counts[1], my_votes);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s_counts[2] = atomicAdd(&a.counters[0], s_counts[0]);
+    s_counts[3] = atomicAdd(&a.counters[1], s_counts[1]);
+    s_counts[6] = (static_cast<int64_t>(s_counts[2]) + s_counts[0] <= a.cap_bins) &&
+                  (static_cast<int64_t>(s_counts[3]) + s_counts[1] <= a.cap_votes);
+    if (!s_counts[6]) a.counters[3] = 1;
+  }
+  __syncthreads();
+  const bool ok = s_counts[6] != 0;
+  const int rec_base = s_counts[2], vote_base = s_counts[3];
+  if (ok) {
+    for (int p = beg + tid; p < end; p += kVoteThreads) {
+      const Rank* rk = reinterpret_cast<const Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+      for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
+        if (rk[o] != 0) return;
+        const int cnt = static_cast<int>(hist[code]);
+        const int rec = rec_base + atomicAdd(&s_counts[4], 1);
+        const int off = vote_base + atomicAdd(&s_counts[5], cnt);
+        a.bin_group[rec] = static_cast<int32_t>(g);
+        a.bin_code[rec] = code;
+        a.bin_count[rec] = cnt;
+        a.bin_offset[rec] = off;
+        hist[code] = static_cast<uint32_t>(off);
+      });
+    }
+  }
+  __syncthreads();
+  if (ok) {
+    for (int p = beg + tid; p < end; p += kVoteThreads) {
+      const int m = a.grouped[p];
+      const Rank* rk = reinterpret_cast<const Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+      for_each_vote(a.base_bin[p], bins, [&](int o, int code) { a.members_raw[hist[code] + rk[o]] = m; });
+    }
+  }
+  __syncthreads();
+  for (int p = beg + tid; p < end; p += kVoteThreads) {
+    const Rank* rk = reinterpret_cast<const Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+    for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
+      if (rk[o] == 0) hist[code] = 0u;
+    });
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteArgs a) {
   extern __shared__ uint32_t hist[];  // bins^4 counters, all zero between groups
-  __shared__ int s_nbins, s_nvotes, s_rec_base, s_vote_base, s_rec_cur, s_vote_cur, s_ok;
-  const Bins4 bins = a.bins;
-  const int nb4 = bins.total();
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int s_counts[8];
+  const int nb4 = a.bins.total();
+  const int tid = threadIdx.x;
   __shared__ int s_chunk, s_nlist;
   __shared__ int s_list[kGroupChunk];
   for (int i = tid; i < nb4; i += kVoteThreads) hist[i] = 0;
@@ -321,87 +401,21 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
       s_list[atomicAdd(&s_nlist, 1)] = tid;
     __syncthreads();
     const int n_list = s_nlist;
-  for (int li = 0; li < n_list; ++li) {
-    const int64_t g = gbase + s_list[li];
-    const int beg = a.group_off[g], end = a.group_off[g + 1];
-    if (tid == 0) s_nbins = s_nvotes = s_rec_cur = s_vote_cur = 0;
-    __syncthreads();
-    // A: count votes; remember which votes hit an empty counter.
-    int my_bins = 0, my_votes = 0;
-    for (int p = beg + tid; p < end; p += kVoteThreads) {
-      unsigned created = 0;
-      for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
-        if (atomicAdd(&hist[code], 1u) == 0u) created |= 1u << o;
-        ++my_votes;
-      });
-      a.creator[p] = static_cast<uint16_t>(created);
-      my_bins += __popc(created);
+    for (int li = 0; li < n_list; ++li) {
+      const int64_t g = gbase + s_list[li];
+      const int beg = a.group_off[g], end = a.group_off[g + 1];
+      if (end - beg <= 65535)
+        vote_space<uint16_t>(a, hist, g, beg, end, s_counts);
+      else
+        vote_space<uint32_t>(a, hist, g, beg, end, s_counts);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      my_bins += __shfl_xor_sync(0xffffffffu, my_bins, o);
-      my_votes += __shfl_xor_sync(0xffffffffu, my_votes, o);
-    }
-    if (lane == 0 && my_votes) {
-      atomicAdd(&s_nbins, my_bins);
-      atomicAdd(&s_nvotes, my_votes);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      s_rec_base = atomicAdd(&a.counters[0], s_nbins);
-      s_vote_base = atomicAdd(&a.counters[1], s_nvotes);
-      s_ok = (static_cast<int64_t>(s_rec_base) + s_nbins <= a.cap_bins) &&
-             (static_cast<int64_t>(s_vote_base) + s_nvotes <= a.cap_votes);
-      if (!s_ok) a.counters[3] = 1;
-    }
-    __syncthreads();
-    const bool ok = s_ok != 0;
-    // B: the creating vote emits the bin record and turns the counter into a write cursor.
-    if (ok) {
-      for (int p = beg + tid; p < end; p += kVoteThreads) {
-        const unsigned created = a.creator[p];
-        if (!created) continue;
-        for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
-          if (!(created >> o & 1u)) return;
-          const int cnt = static_cast<int>(hist[code]);
-          const int rec = s_rec_base + atomicAdd(&s_rec_cur, 1);
-          const int off = s_vote_base + atomicAdd(&s_vote_cur, cnt);
-          a.bin_group[rec] = static_cast<int32_t>(g);
-          a.bin_code[rec] = code;
-          a.bin_count[rec] = cnt;
-          a.bin_offset[rec] = off;
-          hist[code] = static_cast<uint32_t>(off);
-        });
-      }
-    }
-    __syncthreads();
-    // C: every vote appends its match id to its bin.
-    if (ok) {
-      for (int p = beg + tid; p < end; p += kVoteThreads) {
-        const int m = a.grouped[p];
-        for_each_vote(a.base_bin[p], bins,
-                      [&](int, int code) { a.members_raw[atomicAdd(&hist[code], 1u)] = m; });
-      }
-    }
-    __syncthreads();
-    // D: creators clear their counters for the next group.
-    for (int p = beg + tid; p < end; p += kVoteThreads) {
-      const unsigned created = a.creator[p];
-      if (!created) continue;
-      for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
-        if (created >> o & 1u) hist[code] = 0u;
-      });
-    }
-    __syncthreads();
-  }
     __syncthreads();  // s_list / s_chunk are rewritten by the next ticket
   }
 }
 
 struct FinishArgs {
-  sod_scene sc;
-  const int32_t* match_t;
-  const double* pose;
+  const double* pose;        // [M][4]
+  const double* match_size;  // [M][2] model image size of every match (written by hough_pose_kernel)
   const uint32_t* base_bin;
   const int32_t* counters;
   const int32_t* bin_code;
@@ -414,12 +428,15 @@ struct FinishArgs {
   int64_t cap_bins;
   Bins4 bins;
   int detail_min_count;  // bins with fewer votes get no sorted members / means / order key
-  int32_t* big_list;     // bins too large for one thread, finished by hough_finish_big_kernel
-  int32_t* big_count;
+  int32_t* big_list;     // bins of 17 .. kWarpBin votes: one warp each (hough_finish_big_kernel)
+  int32_t* huge_list;    // larger bins: one CTA each (hough_finish_huge_kernel)
+  int32_t* list_count;   // [0] big, [1] huge
   int64_t big_cap;
 };
 
-constexpr int kSmallBin = 16;  // bins up to this size are finished by a single thread
+constexpr int kSmallBin = 16;    // bins up to this size are finished by a single thread
+constexpr int kWarpBin = 1024;   // ... up to this size by one warp, above by one CTA
+constexpr int kFinishThreads = 128;
 
 __device__ __forceinline__ int64_t order_key(const FinishArgs& a, int64_t rec, int first) {
   const uint32_t base = a.base_bin[first];
@@ -434,68 +451,104 @@ __device__ __forceinline__ int64_t order_key(const FinishArgs& a, int64_t rec, i
   return static_cast<int64_t>(first) * 16 + o;
 }
 
-__device__ __forceinline__ double mean_component(const FinishArgs& a, int m, int comp) {
-  if (comp < 4) return a.pose[static_cast<int64_t>(m) * 4 + comp];
-  return a.sc.image_size[2 * a.sc.model_image[a.match_t[m]] + (comp - 4)];
+// The six quantities PoseBin averages for one member: x, y, angle, scale (estimate_object_pose) and the
+// model image's (w, h) - two contiguous rows, no dependent gathers.
+struct Member6 {
+  double v[6];
+};
+__device__ __forceinline__ Member6 load_member(const FinishArgs& a, int m) {
+  const double2* p = reinterpret_cast<const double2*>(a.pose) + static_cast<int64_t>(m) * 2;
+  const double2 p0 = __ldg(p), p1 = __ldg(p + 1), sz = __ldg(reinterpret_cast<const double2*>(a.match_size) + m);
+  return Member6{{p0.x, p0.y, p1.x, p1.y, sz.x, sz.y}};
+}
+// PoseBin.update_* (PoseBin.py:19-43): mean <- (mean * votes + new) / (votes + 1), votes = j members so far.
+__device__ __forceinline__ double running_mean(double mean, double v, int j) {
+  return __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v), static_cast<double>(j + 1));
 }
 
 // One THREAD per bin (almost all bins hold a handful of votes): sort the members by match id (the
-// reference's append order), run the six sequential running means of PoseBin.update_posebin,
-// (old * votes + new) / (votes + 1), and compute the insertion-order key.  Larger bins are queued
-// for the warp-per-bin kernel.
-__global__ void hough_finish_kernel(const FinishArgs a) {
+// reference's append order) in a private strip of shared memory, run the six sequential running means
+// of PoseBin.update_posebin and compute the insertion-order key.  Single-vote bins (the majority) skip
+// the sort; larger bins are queued for the warp-per-bin and CTA-per-bin kernels.
+__global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const FinishArgs a) {
+  __shared__ int s_m[kSmallBin][kFinishThreads + 1];  // column = thread: conflict-free for equal rows
   int64_t n_bins = a.counters[0];
   if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
-  for (int64_t rec = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; rec < n_bins;
+  const int t = threadIdx.x;
+  for (int64_t rec = static_cast<int64_t>(blockIdx.x) * blockDim.x + t; rec < n_bins;
        rec += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int cnt = a.bin_count[rec];
     if (cnt < a.detail_min_count) continue;
     if (cnt > kSmallBin) {
-      const int slot = atomicAdd(a.big_count, 1);
-      if (slot < a.big_cap) a.big_list[slot] = static_cast<int32_t>(rec);
+      const bool huge = cnt > kWarpBin;
+      const int slot = atomicAdd(a.list_count + (huge ? 1 : 0), 1);
+      if (slot < a.big_cap) (huge ? a.huge_list : a.big_list)[slot] = static_cast<int32_t>(rec);
       continue;
     }
     const int off = a.bin_offset[rec];
-    int m[kSmallBin];
+    double mean[6];
+    int first;
+    if (cnt == 1) {
+      first = a.members_raw[off];
+      a.members[off] = first;
+      const Member6 v = load_member(a, first);
 #pragma unroll
-    for (int i = 0; i < kSmallBin; ++i) m[i] = i < cnt ? a.members_raw[off + i] : INT_MAX;
-#pragma unroll
-    for (int i = 1; i < kSmallBin; ++i) {  // insertion sort, fully unrolled: stays in registers
-#pragma unroll
-      for (int j = i; j > 0; --j) {
-        const int lo = min(m[j - 1], m[j]), hi = max(m[j - 1], m[j]);
-        m[j - 1] = lo;
-        m[j] = hi;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kSmallBin; ++i)
-      if (i < cnt) a.members[off + i] = m[i];
-#pragma unroll
-    for (int comp = 0; comp < 6; ++comp) {
-      double mean = 0.0;
-#pragma unroll
-      for (int j = 0; j < kSmallBin; ++j) {
-        if (j < cnt) {
-          const double v = mean_component(a, m[j], comp);
-          mean = j == 0 ? v
-                        : __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v),
-                                    static_cast<double>(j + 1));
+      for (int c = 0; c < 6; ++c) mean[c] = v.v[c];
+    } else {
+      for (int i = 0; i < cnt; ++i) {  // insertion sort: a few elements, runtime bounds, no wasted slots
+        const int x = a.members_raw[off + i];
+        int j = i;
+        while (j > 0 && s_m[j - 1][t] > x) {
+          s_m[j][t] = s_m[j - 1][t];
+          --j;
         }
+        s_m[j][t] = x;
       }
-      a.bin_mean[rec * 6 + comp] = mean;
+      first = s_m[0][t];
+      for (int j = 0; j < cnt; ++j) {
+        const int m = s_m[j][t];
+        a.members[off + j] = m;
+        const Member6 v = load_member(a, m);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) mean[c] = j == 0 ? v.v[c] : running_mean(mean[c], v.v[c], j);
+      }
     }
-    a.bin_order[rec] = order_key(a, rec, m[0]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a.bin_mean[rec * 6 + c] = mean[c];
+    a.bin_order[rec] = order_key(a, rec, first);
   }
 }
 
-// One warp per large bin: rank-sort the members (ids are distinct), then lanes 0..5 each run one
-// of the six sequential running means.
+// The sequential means of one sorted member list by one warp: 32 members are fetched at a time (one per
+// lane, all loads in flight together), then lanes 0..5 each advance one of the six recurrences with the
+// values handed over by shuffles - the dependent chain is the divide, not a memory access.
+__device__ __forceinline__ void warp_means(const FinishArgs& a, const int32_t* sorted, int cnt, int64_t rec, int lane) {
+  double mean = 0.0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int n = min(32, cnt - base);
+    Member6 v;
+    if (lane < n) v = load_member(a, sorted[base + lane]);
+    else v = Member6{{0, 0, 0, 0, 0, 0}};
+    for (int j = 0; j < n; ++j) {
+      double x = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double vc = __shfl_sync(0xffffffffu, v.v[c], j);
+        if (lane == c) x = vc;
+      }
+      if (lane < 6) mean = (base + j) == 0 ? x : running_mean(mean, x, base + j);
+    }
+  }
+  if (lane < 6) a.bin_mean[rec * 6 + lane] = mean;
+  if (lane == 0) a.bin_order[rec] = order_key(a, rec, sorted[0]);
+}
+
+// One warp per bin of 17 .. kWarpBin votes: rank-sort the members (ids are distinct), then the means.
 __global__ void hough_finish_big_kernel(const FinishArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  int64_t n_big = *a.big_count;
+  int64_t n_big = a.list_count[0];
   if (n_big > a.big_cap) n_big = a.big_cap;
   for (int64_t b = warp; b < n_big; b += n_warps) {
     const int64_t rec = a.big_list[b];
@@ -509,17 +562,94 @@ __global__ void hough_finish_big_kernel(const FinishArgs a) {
       out[rank] = x;
     }
     __syncwarp();
-    if (lane < 6) {
-      double mean = 0.0;
-      for (int j = 0; j < cnt; ++j) {
-        const double v = mean_component(a, out[j], lane);
-        mean = j == 0 ? v
-                      : __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v),
-                                  static_cast<double>(j + 1));
-      }
-      a.bin_mean[rec * 6 + lane] = mean;
+    warp_means(a, out, cnt, rec, lane);
+  }
+}
+
+// One CTA per bin of more than kWarpBin votes (a dominant object in a single Hough space can put 10^4-10^5
+// matches into one bin).  Match ids are distinct, so the sort is a bitmap: windows of kWindowBits
+// consecutive ids are marked in shared memory and read back in order - O(votes + id range) instead of the
+// O(votes^2) of a rank sort.  The running means stay one sequential chain (the reference's recurrence is
+// order dependent), fed by warp 0 through warp_means.
+constexpr int kHugeThreads = 1024;
+constexpr int kWindowWords = 32768;                 // 128 KB of shared memory
+constexpr int64_t kWindowBits = int64_t(kWindowWords) * 32;
+
+__global__ void __launch_bounds__(kHugeThreads, 1) hough_finish_huge_kernel(const FinishArgs a) {
+  extern __shared__ uint32_t bitmap[];
+  __shared__ int s_lo, s_hi, s_warp_tot[32], s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t n_huge = a.list_count[1];
+  if (n_huge > a.big_cap) n_huge = a.big_cap;
+  for (int64_t b = blockIdx.x; b < n_huge; b += gridDim.x) {
+    const int64_t rec = a.huge_list[b];
+    const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
+    const int32_t* raw = a.members_raw + off;
+    int32_t* out = a.members + off;
+    if (tid == 0) { s_lo = INT_MAX; s_hi = INT_MIN; s_base = 0; }
+    __syncthreads();
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int i = tid; i < cnt; i += kHugeThreads) {
+      const int x = raw[i];
+      lo = min(lo, x);
+      hi = max(hi, x);
     }
-    if (lane == 0) a.bin_order[rec] = order_key(a, rec, out[0]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    __syncthreads();
+    const int id_lo = s_lo, id_hi = s_hi;
+    for (int64_t w0 = id_lo; w0 <= id_hi; w0 += kWindowBits) {
+      for (int i = tid; i < kWindowWords; i += kHugeThreads) bitmap[i] = 0u;
+      __syncthreads();
+      for (int i = tid; i < cnt; i += kHugeThreads) {
+        const int64_t d = static_cast<int64_t>(raw[i]) - w0;
+        if (d >= 0 && d < kWindowBits) atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+      }
+      __syncthreads();
+      // every thread owns kWindowWords / kHugeThreads consecutive words: count, scan over the CTA, emit
+      constexpr int kPer = kWindowWords / kHugeThreads;
+      int mine = 0;
+#pragma unroll 4
+      for (int k = 0; k < kPer; ++k) mine += __popc(bitmap[tid * kPer + k]);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_warp_tot[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        int wv = s_warp_tot[lane], wi = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, wi, o);
+          if (lane >= o) wi += v;
+        }
+        s_warp_tot[lane] = wi - wv;  // exclusive
+      }
+      __syncthreads();
+      int pos = s_base + s_warp_tot[warp] + incl - mine;
+      for (int k = 0; k < kPer; ++k) {
+        uint32_t word = bitmap[tid * kPer + k];
+        while (word) {
+          const int bit = __ffs(word) - 1;
+          word &= word - 1;
+          out[pos++] = static_cast<int32_t>(w0 + (static_cast<int64_t>(tid * kPer + k) << 5) + bit);
+        }
+      }
+      __syncthreads();
+      if (tid == kHugeThreads - 1) s_base = pos;  // the last thread's end = the window's total
+      __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (warp == 0) warp_means(a, out, cnt, rec, lane);
+    __syncthreads();
   }
 }
 
@@ -580,10 +710,10 @@ compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict_
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
-  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket, *big_list;
-  uint32_t* grouped_base;
+  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket, *big_list, *huge_list;
+  uint32_t *grouped_base, *rank;
+  double* match_size;
   int64_t big_cap;
-  uint16_t* creator;
   size_t bytes;
 };
 
@@ -602,10 +732,12 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.group_cursor = static_cast<int32_t*>(take((groups + 1) * 4));
   w.grouped = static_cast<int32_t*>(take(m * 4));
   w.grouped_base = static_cast<uint32_t*>(take(m * 4));
-  w.creator = static_cast<uint16_t*>(take(m * 2));
+  w.rank = static_cast<uint32_t*>(take(m * 16 * 4));
+  w.match_size = static_cast<double*>(take(m * 2 * 8));
   w.members_raw = static_cast<int32_t*>(take(cap_votes * 4));
   w.big_cap = cap_votes / (kSmallBin + 1) + 1;
   w.big_list = static_cast<int32_t*>(take(w.big_cap * 4));
+  w.huge_list = static_cast<int32_t*>(take((cap_votes / (kWarpBin + 1) + 1) * 4));
   w.bytes = o;
   return w;
 }
@@ -663,6 +795,7 @@ int sod_estimate_pose(const sod_scene* scene, const int32_t* match_q, const int3
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = nullptr; pa.n_cap = n_matches;
   pa.bins = Bins4{bins, bins, bins, bins}; pa.sigma_lut = sigma_lut; pa.pose = pose; pa.base_bin = base_bin;
   pa.near_edge = near_edge; pa.counters = nullptr; pa.group_of = nullptr; pa.group_count = nullptr;
+  pa.match_size = nullptr;
   const int threads = 256;
   hough_pose_kernel<<<static_cast<unsigned>((n_matches + threads - 1) / threads), threads, 0,
                       static_cast<cudaStream_t>(stream)>>>(pa);
@@ -737,13 +870,13 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   if (sms <= 0) return SOD_ERR_CUDA;
 
   SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_groups + 1) * 4, st));
-  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 8, st));  // [0] vote ticket, [1] big-bin count
+  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 12, st));  // [0] vote ticket, [1] big-bin count, [2] huge-bin count
   PoseArgs pa;
   pa.sc = *scene;
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = n_matches_dev; pa.n_cap = n_matches;
   pa.bins = bins; pa.sigma_lut = sigma_lut; pa.pose = out->pose; pa.base_bin = out->base_bin;
   pa.near_edge = out->near_edge; pa.counters = out->counters; pa.group_of = w.group_of;
-  pa.group_count = w.group_count;
+  pa.group_count = w.group_count; pa.match_size = w.match_size;
   const int threads = 256;
   int64_t blocks = (n_matches + threads - 1) / threads;
   if (blocks > static_cast<int64_t>(sms) * 16) blocks = static_cast<int64_t>(sms) * 16;
@@ -758,7 +891,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   stage_end(SOD_STAGE_HOUGH_PREP, st);
 
   VoteArgs va;
-  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.creator = w.creator;
+  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.rank = w.rank;
   va.n_groups = n_groups; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
@@ -777,18 +910,22 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   SOD_CHECK_LAUNCH("hough_vote_kernel");
 
   FinishArgs fa;
-  fa.sc = *scene;
-  fa.match_t = match_t; fa.pose = out->pose; fa.base_bin = out->base_bin; fa.counters = out->counters;
+  fa.pose = out->pose; fa.match_size = w.match_size; fa.base_bin = out->base_bin; fa.counters = out->counters;
   fa.bin_code = out->bin_code; fa.bin_count = out->bin_count; fa.bin_offset = out->bin_offset;
   fa.members_raw = w.members_raw; fa.members = out->members; fa.bin_order = out->bin_order;
   fa.bin_mean = out->bin_mean; fa.cap_bins = out->cap_bins; fa.bins = bins;
-  fa.detail_min_count = detail_min_count; fa.big_list = w.big_list; fa.big_count = w.ticket + 1;
+  fa.detail_min_count = detail_min_count; fa.big_list = w.big_list; fa.huge_list = w.huge_list;
+  fa.list_count = w.ticket + 1;
   fa.big_cap = w.big_cap;
   stage_begin(SOD_STAGE_HOUGH_FINISH, st);
-  hough_finish_kernel<<<sms * 8, 256, 0, st>>>(fa);
+  hough_finish_kernel<<<sms * 16, kFinishThreads, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_kernel");
   hough_finish_big_kernel<<<sms * 8, 256, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_big_kernel");
+  constexpr int kHugeSmem = kWindowWords * 4;
+  SOD_CHECK_CUDA(cudaFuncSetAttribute(hough_finish_huge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHugeSmem));
+  hough_finish_huge_kernel<<<sms, kHugeThreads, kHugeSmem, st>>>(fa);
+  SOD_CHECK_LAUNCH("hough_finish_huge_kernel");
   stage_end(SOD_STAGE_HOUGH_FINISH, st);
   return SOD_OK;
 }

@@ -114,7 +114,7 @@ class DetectionPipeline:
         sweep_stages (seeded runs only): the shard sweep runs in this many tile ranges with a MIN all-reduce
         of the thresholds between them - after half of every shard the bound is the best 2nd best any rank
         has seen in half of the WHOLE database (B200, 8 x 125k rows: 14.5 ms in two stages against 15.7 ms
-        in one, profiles/r02_seed_staged.txt); None = 2.
+        in one, profiles/r02_seed_staged.txt); None = 2 for shards of up to 262,144 rows, else 1.
         replicated_host (shard="db", several ranks): every rank is handed the same HOST batch, so each
         uploads only its 1/G slice of the rows over its own PCIe link and one all-gather over NVLink
         replicates it on the devices (load_queries); False = every rank uploads the whole batch.
@@ -137,7 +137,7 @@ class DetectionPipeline:
         self.exchange = exchange
         self.replicated_host, self.result_rows = bool(replicated_host), result_rows
         self.seed_min_queries = SEED_MIN_QUERIES
-        self.sweep_stages = 2 if sweep_stages is None else max(1, int(sweep_stages))
+        self._sweep_stages_arg = sweep_stages
         self.shard_mode = shard
         if shard == "frames":
             rank, world = 0, 1
@@ -188,6 +188,10 @@ class DetectionPipeline:
                 sample = db.des[torch.from_numpy(rows)] if isinstance(db.des, torch.Tensor) else \
                     torch.from_numpy(np.ascontiguousarray(np.asarray(db.des)[rows]))
                 self.seed_matcher = E.Matcher(E.prepare_db(sample.to(self.device).contiguous(), index_base=0))
+        # two stages pay on short shard sweeps (<= 256k rows: 8 ranks x 125k gain 1.1 ms of 15.7); on a 500k-row
+        # shard the second launch costs what the tighter bound saves (measured at 2 ranks)
+        self.sweep_stages = (2 if self.row_hi - self.row_lo <= 262144 else 1) if self._sweep_stages_arg is None \
+            else max(1, int(self._sweep_stages_arg))
         self.max_queries = int(max_queries)
         # capacity of the query-side buffers: whole slices of ceil(n / world) rows for every n <= max_queries
         nq = self.max_queries + (world - 1 if world > 1 else 0)
@@ -235,7 +239,7 @@ class DetectionPipeline:
         # our kernels per detect_device call; the key exchange of a database-sharded run is
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
-        self.launches_per_call = 16 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
+        self.launches_per_call = 17 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
             (3 + (3 if self.sweep_stages > 1 else 0) if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs

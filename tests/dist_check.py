@@ -57,7 +57,8 @@ def main():
                                     replicated_host=False).detect(*q), "whole-batch upload")
     # the same with threshold seeding forced on (it is automatic only for large databases and batches): a
     # replicated 1024-row sample, each rank seeds 1/G of the query rows, one min-reduce, then the shard sweep
-    seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024)
+    seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024,
+                                    sweep_stages=2)
     seeded_pipe.seed_min_queries = 0
     assert seeded_pipe.seed_matcher is not None
     assert seeded_pipe.sweep_stages == 2                     # the shard sweep in two ranges + a mid all-reduce

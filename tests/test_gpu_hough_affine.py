@@ -353,3 +353,48 @@ def test_matches_on_bin_boundaries_are_resolved_bit_exactly():
     want = np.array([O.bin_index(scene.pose_of(i, i), 15, scene.height, scene.width) for i in range(n)])
     got = res.base_bin[:n].cpu().numpy().astype(np.int64)
     np.testing.assert_array_equal(np.stack([got & 0xFF, got >> 8 & 0xFF, got >> 16 & 0xFF, got >> 24], 1), want)
+
+
+def test_one_bin_with_60k_votes_single_space():
+    """Round-1 advisor finding: with the reference's single Hough space a dominant object puts 10^4-10^5
+    matches into ONE bin.  60,000 matches of one rigid instance (+ 5,000 scattered ones): members of every
+    bin ascending (the reference's append order), counts and running means equal to the oracle's
+    sequential recurrence; the CTA-per-bin bitmap sort and the warp-fed mean chain do the work."""
+    from sod_b200 import engine as E
+    rng = np.random.default_rng(77)
+    n_in, n_out = 60_000, 5_000
+    n = n_in + n_out
+    W, H = 4032, 3024
+    m_xy = rng.uniform(0, 1500, (n, 2)).astype(np.float32)
+    cent = np.array([[750.0, 500.0]])
+    q_xy = np.empty((n, 2), np.float32)
+    q_xy[:n_in] = m_xy[:n_in] + np.float32([1000.25, 800.5])          # scale 1, no rotation: one pose for all
+    q_xy[n_in:] = np.stack([rng.uniform(0, W, n_out), rng.uniform(0, H, n_out)], 1)
+    ang = rng.uniform(0, 360, n).astype(np.float32)
+    q_ang = ang.copy()
+    q_ang[n_in:] = rng.uniform(0, 360, n_out).astype(np.float32)
+    octv = scenes.pack_octave(np.ones(n, np.int64), np.ones(n, np.int64))
+    perm = rng.permutation(n)                                          # inliers and outliers interleaved
+    q_xy, q_ang, m_xy, ang = q_xy[perm], q_ang[perm], m_xy[perm], ang[perm]
+    size = np.array([[1500.0, 1000.0]])
+    sc = E.SceneArrays(q_xy, q_ang, octv, m_xy, ang, octv, np.zeros(n, np.int32), cent, size,
+                       np.array([[W, H]], np.int32))
+    ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    res = E.HoughVoter(sc, 15).vote(ids, ids)
+    h = res.host()
+    assert h["n_unresolved_edge"] == 0
+    big = np.flatnonzero(h["count"] >= n_in)
+    assert len(big) == 16 and h["count"].max() <= n
+    scene = O.Scene(q_xy, q_ang, octv, m_xy, ang, octv, np.zeros(n, np.int32), cent, size, W, H)
+    table = O.hough_vote(scene, np.arange(n), np.arange(n), 15)
+    np.testing.assert_array_equal(_decode(h["code"], 15), np.array([k[1:] for k in table.keys()]))
+    np.testing.assert_array_equal(h["count"], [b.votes for b in table.values()])
+    want_means = np.array([[b.centroid[0], b.centroid[1], b.angle, b.scale, b.img_size[0], b.img_size[1]]
+                           for b in table.values()])
+    np.testing.assert_allclose(h["mean"], want_means, rtol=1e-12, atol=1e-9)
+    for i, b in enumerate(table.values()):
+        if h["count"][i] >= 17:                                        # warp- and CTA-finished bins
+            np.testing.assert_array_equal(h["members"][h["offset"][i]:h["offset"][i] + h["count"][i]], b.members)
+    # the affine stage on the same result: the giant bins survive with (nearly) all inliers
+    aff = E.affine_verify(sc, ids, ids, res, 5, 4).host(h["n_votes"])
+    assert (aff["votes"][aff["live"]] >= n_in).sum() >= 1
