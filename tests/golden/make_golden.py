@@ -264,7 +264,75 @@ def make_affine_singular(width=4032, height=3024, threshold=4):
     print("affine_singular:", len(cases), "bins,", int(np.sum(live)), "live,", int(np.sum(keep)), "of", len(keep), "pairs kept")
 
 
+def synthetic_image(seed, width, height):
+    """Multi-octave noise + random circles / rectangles: texture on which SIFT finds
+    keypoints on several octaves, many of them with more than one orientation."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = np.zeros((height, width), np.float32)
+    for octv in range(6):
+        h, w = max(height >> octv, 2), max(width >> octv, 2)
+        img += cv2.resize(rng.normal(0, 1, (h, w)).astype(np.float32), (width, height), interpolation=cv2.INTER_CUBIC) * (1.6 ** octv)
+    img = (img - img.min()) / (img.max() - img.min()) * 160 + 40
+    img = img.astype(np.uint8)
+    for _ in range(max(width * height // 9000, 20)):
+        c = int(rng.integers(0, 256))
+        x, y = int(rng.integers(0, width)), int(rng.integers(0, height))
+        if rng.random() < 0.5:
+            cv2.circle(img, (x, y), int(rng.integers(4, 40)), c, -1 if rng.random() < 0.6 else 2)
+        else:
+            cv2.rectangle(img, (x, y), (x + int(rng.integers(6, 70)), y + int(rng.integers(6, 70))), c,
+                          -1 if rng.random() < 0.6 else 2)
+    return cv2.GaussianBlur(img, (0, 0), 0.8)
+
+
+def make_c1(model_wh=(1500, 1000), scene_wh=(2000, 1500), scale=0.5, angle_deg=25.0):
+    """tests/golden/scene_c1.npz - BASELINE configs[0] (main.py as shipped) on a synthetic image pair,
+    because the reference's dataset and pickle are not available: a textured model image is pasted at
+    `scale` / `angle_deg` into a clutter scene, REAL cv2.SIFT_create() keypoints and descriptors on both
+    sides (GenerateDatabaseInfo.py:14-34, main.py:36-46 with the reference's own get_centroid), then the
+    unmodified reference Main from run_matcher to post_process.  Pins real octave packing (negative
+    octaves, layers) and multi-orientation duplicates (several keypoints at one location)."""
+    import cv2
+    refmain = import_reference()
+    from SiftHelperFunctions import get_centroid
+    mw, mh = model_wh
+    sw, sh = scene_wh
+    model = synthetic_image(1, mw, mh)
+    scene_img = synthetic_image(2, sw, sh)
+    rot = cv2.getRotationMatrix2D((mw / 2, mh / 2), angle_deg, scale)
+    rot[:, 2] += np.array([sw / 2 - mw / 2, sh / 2 - mh / 2])
+    warped = cv2.warpAffine(model, rot, (sw, sh), flags=cv2.INTER_LINEAR)
+    mask = cv2.warpAffine(np.full((mh, mw), 255, np.uint8), rot, (sw, sh)) > 127
+    scene_img[mask] = warped[mask]
+    sift = cv2.SIFT_create()
+    kp_m, des_m = sift.detectAndCompute(model, None)
+    kp_q, des_q = sift.detectAndCompute(scene_img, None)
+    assert np.array_equal(des_m, np.rint(des_m)) and des_m.max() <= 255
+    arr = lambda kps, f: np.array([f(k) for k in kps])  # noqa: E731
+    sc = scenes.SyntheticScene(
+        m_des=des_m.astype(np.uint8), m_xy=arr(kp_m, lambda k: k.pt).astype(np.float32),
+        m_angle=arr(kp_m, lambda k: k.angle).astype(np.float32), m_octave=arr(kp_m, lambda k: k.octave).astype(np.int32),
+        m_size=arr(kp_m, lambda k: k.size).astype(np.float32), m_image=np.zeros(len(kp_m), np.int32),
+        img_size=np.array([[mw, mh]], np.int32), img_centroid=np.array([get_centroid(kp_m)], np.float64),
+        q_des=des_q.astype(np.uint8), q_xy=arr(kp_q, lambda k: k.pt).astype(np.float32),
+        q_angle=arr(kp_q, lambda k: k.angle).astype(np.float32), q_octave=arr(kp_q, lambda k: k.octave).astype(np.int32),
+        q_size=arr(kp_q, lambda k: k.size).astype(np.float32), width=sw, height=sh,
+        true_q=np.zeros(0, np.int32), true_t=np.zeros(0, np.int32))
+    out = run_reference(refmain, sc)
+    dup = len(sc.m_xy) - len(np.unique(sc.m_xy, axis=0))
+    inputs = {f"in_{k}": v for k, v in sc.__dict__.items()}
+    np.savez_compressed(HERE / "scene_c1.npz", **inputs, **out, paste=np.array([scale, angle_deg]),
+                        versions=np.array([cv2.__version__, np.__version__, sys.version.split()[0]]))
+    octs = np.unique((sc.m_octave & 0xFF).astype(np.int8))
+    print("scene_c1: model kp", len(kp_m), "scene kp", len(kp_q), "duplicate model locations", dup, "octaves", octs.tolist(),
+          "matches", len(out["match_q"]), "bins", len(out["bin_votes"]), "valid", len(out["valid_keys"]), "live",
+          len(out["live_keys"]), "final", out["final_pose"].round(2).tolist())
+
+
 def main():
+    if "--c1-only" in sys.argv:
+        return make_c1()
     if "--postprocess-only" in sys.argv:
         return make_postprocess()
     if "--affine-singular-only" in sys.argv:
@@ -282,6 +350,7 @@ def main():
 
     make_postprocess()
     make_affine_singular()
+    make_c1()
 
     # known-answer facts taken from the reference's own libraries
     import math

@@ -29,7 +29,7 @@ def _main_for(z):
     return m
 
 
-@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny"])
+@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny", "scene_c1"])
 def test_main_flow_equals_reference(name):
     z = np.load(GOLD / f"{name}.npz")
     m = _main_for(z)

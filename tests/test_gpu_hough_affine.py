@@ -33,7 +33,7 @@ def _decode(code, bins):
     return out
 
 
-@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny"])
+@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny", "scene_c1"])
 def test_hough_matches_reference_golden(name):
     from sod_b200 import engine as E
     z = np.load(GOLD / f"{name}.npz")
@@ -63,7 +63,7 @@ def test_hough_matches_reference_golden(name):
     np.testing.assert_allclose(res.pose[:len(want)].cpu().numpy(), want, rtol=1e-13, atol=1e-10)
 
 
-@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny"])
+@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny", "scene_c1"])
 def test_affine_matches_reference_golden(name):
     from sod_b200 import engine as E
     z = np.load(GOLD / f"{name}.npz")

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
 
 
-@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny"])
+@pytest.mark.parametrize("name", ["scene_single", "scene_multi", "scene_tiny", "scene_c1"])
 def test_pipeline_to_final_pose_equals_reference(name):
     from sod_b200.pipeline import DetectionPipeline, ModelDatabase
     z = np.load(GOLD / f"{name}.npz")

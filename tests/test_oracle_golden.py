@@ -8,7 +8,7 @@ import pytest
 from oracle import sod_oracle as O
 
 GOLD = Path(__file__).resolve().parent / "golden"
-SCENES = ["scene_single", "scene_multi", "scene_tiny"]
+SCENES = ["scene_single", "scene_multi", "scene_tiny", "scene_c1"]
 
 
 def load(name):
