@@ -26,6 +26,8 @@
 // by original index and a permutation maps back, so results (incl. ties -> lowest original index,
 // as cv2) do not depend on the reordering.
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "sod_common.cuh"
@@ -35,6 +37,10 @@
 
 namespace sod {
 namespace {
+
+#ifndef SOD_MATCH_CTA_PAIR_DEFAULT
+#define SOD_MATCH_CTA_PAIR_DEFAULT 0
+#endif
 
 constexpr int kTileM = 128;                 // query rows per MMA (TMEM lanes)
 constexpr int kHalves = 2;                  // query tiles per CTA sharing one database tile
@@ -62,16 +68,24 @@ constexpr int kRegsLaunch = 65536 / kThreads / 8 * 8;
 static_assert(128 * kRegsLight + kEpiWarps * 32 * kRegsEpilogue <= kThreads * kRegsLaunch,
               "setmaxnreg budget exceeds the CTA's register pool");
 
-constexpr int kOffA = 0;                                    // [2 buffers][2 halves][16 KB]
-constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;     // [kStages][16 KB]
-constexpr int kOffCq = kOffB + kStages * kTileBytes;        // [kCqSlots][128] int32
-constexpr int kOffBar = kOffCq + kCqSlots * kCqTileBytes;
 constexpr int kBarGroups = kParity;  // accumulator barriers are indexed by step % kBarGroups: every barrier is
                                      // then waited on by ONE set of epilogue warps for consecutive phases (a
                                      // parity wait must never skip a phase)
-constexpr int kNumBars = 2 * kStages + 4 + 4 * kBarGroups + kCqSlots;
-constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // +1024: manual 1 KB alignment
+// Shared-memory layout.  kPair = the CTA-pair form (cta_group::2): a CTA holds HALF of every database tile
+// (64 rows, 8 KB), so its ring is deeper for the same bytes in flight.
+template <bool kPair>
+struct Layout {
+  static constexpr int kStagesL = kPair ? 8 : kStages;
+  static constexpr int kBStageBytes = kPair ? kTileBytes / 2 : kTileBytes;
+  static constexpr int kCqSlotsL = kStagesL + 6;            // see the slot-reuse argument in the producer
+  static constexpr int kOffA = 0;                                     // [2 buffers][2 halves][16 KB]
+  static constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;      // [stages][16 KB | 8 KB]
+  static constexpr int kOffCq = kOffB + kStagesL * kBStageBytes;      // [cq slots][260] int32
+  static constexpr int kOffBar = kOffCq + kCqSlotsL * kCqTileBytes;
+  static constexpr int kNumBars = 2 * kStagesL + 4 + 4 * kBarGroups + kCqSlotsL;
+  static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;          // +1024: manual 1 KB alignment
+};
 
 struct MatchArgs {
   const int32_t* qn;   // [nq] |q|^2
@@ -84,6 +98,7 @@ struct MatchArgs {
   int n_tiles;         // tiles swept by this launch: [tile_begin, tile_begin + n_tiles)
   int tile_begin;
   int n_qblocks;
+  int n_qunits;        // query blocks per unit row: n_qblocks, or ceil(n_qblocks / 2) CTA pairs
   int n_seg;
   int idx_base;
 };
@@ -170,10 +185,20 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
 // run), which have nobody to share with inside the launch and must not pay the per-tile load and
 // atomicMin of the sharing code (B200, 1.28 M queries x 125k-row shard: 15.27 ms against 16.21 ms
 // with the sharing instance and 16.44 ms unseeded; profiles/r02_threshold_seeding.txt).
-template <bool kShare, bool kSeeded = false>
+// kPair: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 per query half over
+// M = 256 rows - 128 query rows of each CTA - and N = 128 database rows, of which each CTA stages 64: the
+// database stream from L2 and the shared-memory operand reads per MAC drop (B: 8 KB instead of 16 KB per
+// CTA and tile), the accumulators and the whole epilogue stay per CTA exactly as in the single-CTA form.
+// The leader CTA (cluster rank 0) issues the MMAs; TMA loads of both CTAs report to the leader's "full"
+// barriers, tcgen05.commit multicasts "free" / "accumulator ready" to both CTAs, and the epilogue warps of
+// both CTAs release accumulator slots on the leader's barriers.
+template <bool kShare, bool kSeeded = false, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_db, const MatchArgs a) {
+  using L = Layout<kPair>;
+  constexpr int kSt = L::kStagesL;
+  constexpr int kCqS = L::kCqSlotsL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1 KB alignment
@@ -181,24 +206,27 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit0 = kPair ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int unit_step = kPair ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
 
-  const uint32_t bar0 = base + kOffBar;
+  const uint32_t bar0 = base + L::kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto bar_afull = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
-  auto bar_aempty = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kSt + s); };
+  auto bar_afull = [&](int b) { return bar0 + 8u * (2 * kSt + b); };
+  auto bar_aempty = [&](int b) { return bar0 + 8u * (2 * kSt + 2 + b); };
   // accumulator hand-off barriers per (step % kBarGroups, half); the TMEM slot itself is step & 1
-  auto bar_tfull = [&](int g, int h) { return bar0 + 8u * (2 * kStages + 4 + 2 * g + h); };
-  auto bar_tempty = [&](int g, int h) { return bar0 + 8u * (2 * kStages + 4 + 2 * kBarGroups + 2 * g + h); };
-  auto bar_cqfull = [&](int s) { return bar0 + 8u * (2 * kStages + 4 + 4 * kBarGroups + s); };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  auto bar_tfull = [&](int g, int h) { return bar0 + 8u * (2 * kSt + 4 + 2 * g + h); };
+  auto bar_tempty = [&](int g, int h) { return bar0 + 8u * (2 * kSt + 4 + 2 * kBarGroups + 2 * g + h); };
+  auto bar_cqfull = [&](int s) { return bar0 + 8u * (2 * kSt + 4 + 4 * kBarGroups + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_db);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kSt; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), kHalves);  // one tcgen05.commit per issuing warp
     }
@@ -209,21 +237,26 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int g = 0; g < kBarGroups; ++g)
       for (int h = 0; h < kHalves; ++h) {
         mbar_init(bar_tfull(g, h), 1);
-        mbar_init(bar_tempty(g, h), 4);  // the four quadrant warps that read one slot
+        mbar_init(bar_tempty(g, h), kPair ? 8 : 4);  // the four quadrant warps that read one slot (of each CTA)
       }
-    for (int s = 0; s < kCqSlots; ++s) mbar_init(bar_cqfull(s), 1);
+    for (int s = 0; s < kCqS; ++s) mbar_init(bar_cqfull(s), 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_units = a.n_qblocks * a.n_seg;
+  const int total_units = a.n_qunits * a.n_seg;
 
   if (warp < 4) {
     if constexpr (kRegsLight < kRegsLaunch)
@@ -232,35 +265,54 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t step = 0, ucount = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
-        const int seg = u / a.n_qblocks;
-        const int qb = u - seg * a.n_qblocks;
+      for (int u = unit0; u < total_units; u += unit_step, ++ucount) {
+        const int seg = u / a.n_qunits;
+        const int qu = u - seg * a.n_qunits;
+        const int qb = kPair ? qu * 2 + static_cast<int>(cta_rank) : qu;
         const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
         const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
         const uint32_t ab = ucount & 1u, aph = (ucount >> 1) & 1u;
         mbar_wait(bar_aempty(ab), aph ^ 1u);
-        mbar_arrive_expect_tx(bar_afull(ab), kHalves * kTileBytes);
-        for (int h = 0; h < kHalves; ++h)
-          tma_load_2d(base + kOffA + (ab * kHalves + h) * kTileBytes, &tmap_q, bar_afull(ab), 0,
-                      qb * kBlockQ + h * kTileM);
+        if constexpr (kPair) {
+          // both CTAs' query blocks report to the leader's barrier, which expects the bytes of both
+          if (cta_rank == 0) mbar_arrive_expect_tx(bar_afull(ab), 2 * kHalves * kTileBytes);
+          const uint32_t afull_leader = mapa_shared(bar_afull(ab), 0);
+          for (int h = 0; h < kHalves; ++h)
+            tma_load_2d_pair(base + L::kOffA + (ab * kHalves + h) * kTileBytes, &tmap_q, afull_leader, 0,
+                             qb * kBlockQ + h * kTileM);
+        } else {
+          mbar_arrive_expect_tx(bar_afull(ab), kHalves * kTileBytes);
+          for (int h = 0; h < kHalves; ++h)
+            tma_load_2d(base + L::kOffA + (ab * kHalves + h) * kTileBytes, &tmap_q, bar_afull(ab), 0,
+                        qb * kBlockQ + h * kTileM);
+        }
         for (int t = t0; t < t1; ++t, ++step) {
-          const uint32_t s = step % kStages, ph = (step / kStages) & 1u;
+          const uint32_t s = step % kSt, ph = (step / kSt) & 1u;
           mbar_wait(bar_empty(s), ph ^ 1u);
-          mbar_arrive_expect_tx(bar_full(s), kTileBytes);
-          tma_load_2d(base + kOffB + s * kTileBytes, &tmap_db, bar_full(s), 0, t * kTileN);
+          if constexpr (kPair) {
+            // this CTA stages rows [64 * rank, 64 * rank + 64) of the tile
+            if (cta_rank == 0) mbar_arrive_expect_tx(bar_full(s), 2 * L::kBStageBytes);
+            tma_load_2d_pair(base + L::kOffB + s * L::kBStageBytes, &tmap_db, mapa_shared(bar_full(s), 0), 0,
+                             t * kTileN + static_cast<int>(cta_rank) * (kTileN / 2));
+          } else {
+            mbar_arrive_expect_tx(bar_full(s), kTileBytes);
+            tma_load_2d(base + L::kOffB + s * kTileBytes, &tmap_db, bar_full(s), 0, t * kTileN);
+          }
           // cq slice rides in its own, deeper ring: stage s is released when the MMAs that read it
           // retire, but the epilogue still reads cq after it has handed the accumulator back.
           // The write for step j happens after MMA(j-kStages) retired; that MMA was issued after
           // every epilogue warp RELEASED step j-kStages-2, i.e. finished its arithmetic on step
           // j-kStages-3.  Steps j-kStages-2 .. j-1 may still be live -> kStages+3 slots are needed.
-          const uint32_t slot = step % kCqSlots;
+          // (Pair form: every CTA needs the constants of the WHOLE tile - its accumulators span all 128
+          // database rows - and loads them itself; the argument holds per CTA because the MMAs are joint.)
+          const uint32_t slot = step % kCqS;
           mbar_arrive_expect_tx(bar_cqfull(slot), kCqTileBytes);
-          bulk_load_1d(base + kOffCq + slot * kCqTileBytes, a.cq + static_cast<int64_t>(t) * kCqTile,
+          bulk_load_1d(base + L::kOffCq + slot * kCqTileBytes, a.cq + static_cast<int64_t>(t) * kCqTile,
                        kCqTileBytes, bar_cqfull(slot));
         }
       }
     }
-  } else if (warp == 1 || warp == 3) {
+  } else if ((warp == 1 || warp == 3) && cta_rank == 0) {
     // ------------------------------------------------------------------ MMA issuers
     // Two issuing warps, one per query half (warp 1 -> half 0, warp 3 -> half 1): with K = 128 an
     // accumulator slot holds only 256 clk of tensor work, so the issuing warp's own instruction
@@ -269,19 +321,19 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // tcgen05 instructions are issued by one elected lane.  (Inside a divergent `if (lane == 0)`
     // every UTCIMMA operand needs an R2UR move.)
     const int h = warp >> 1;
-    constexpr uint32_t idesc = umma_idesc_u8(kTileM, kTileN);
+    constexpr uint32_t idesc = umma_idesc_u8(kPair ? 2 * kTileM : kTileM, kTileN);
     uint32_t step = 0, ucount = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
-      const int seg = u / a.n_qblocks;
+    for (int u = unit0; u < total_units; u += unit_step, ++ucount) {
+      const int seg = u / a.n_qunits;
       const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
       const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const uint32_t ab = ucount & 1u, aph = (ucount >> 1) & 1u;
       mbar_wait(bar_afull(ab), aph);
-      const uint64_t adesc = umma_desc_k128(base + kOffA + (ab * kHalves + h) * kTileBytes);
+      const uint64_t adesc = umma_desc_k128(base + L::kOffA + (ab * kHalves + h) * kTileBytes);
       for (int t = t0; t < t1; ++t, ++step) {
-        const uint32_t s = step % kStages, ph = (step / kStages) & 1u;
+        const uint32_t s = step % kSt, ph = (step / kSt) & 1u;
         const uint32_t acc = step & 1u;
-        const uint64_t bdesc = umma_desc_k128(base + kOffB + s * kTileBytes);
+        const uint64_t bdesc = umma_desc_k128(base + L::kOffB + s * L::kBStageBytes);
         const uint32_t d = tmem_base + acc * (kHalves * kTileN) + h * kTileN;
         mbar_wait(bar_full(s), ph);
         if (step >= 2)  // slot step & 1 was last used by step - 2: wait for its epilogue warps' release
@@ -289,14 +341,24 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < SOD_DESC_DIM / 32; ++k)  // K = 32 bytes per UTCIMMA: +2 x 16 B
-            umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          umma_commit(bar_tfull(step % kBarGroups, h));  // this half is ready for its epilogue warps
-          umma_commit(bar_empty(s));       // (count 2) database stage free once both halves retire
+          for (int k = 0; k < SOD_DESC_DIM / 32; ++k) {  // K = 32 bytes per UTCIMMA: +2 x 16 B
+            if constexpr (kPair) umma_i8_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+            else umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+          }
+          if constexpr (kPair) {
+            umma_commit_pair(bar_tfull(step % kBarGroups, h), 3);  // this half is ready in both CTAs
+            umma_commit_pair(bar_empty(s), 3);   // (count 2) stage free in both CTAs once both halves retire
+          } else {
+            umma_commit(bar_tfull(step % kBarGroups, h));  // this half is ready for its epilogue warps
+            umma_commit(bar_empty(s));       // (count 2) database stage free once both halves retire
+          }
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(bar_aempty(ab));  // (count 2) query block buffer free
+      if (elect_one()) {  // (count 2) query block buffer free
+        if constexpr (kPair) umma_commit_pair(bar_aempty(ab), 3);
+        else umma_commit(bar_aempty(ab));
+      }
       __syncwarp();
     }
   }
@@ -308,10 +370,14 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int h = (e >> 2) & 1;         // which query half-tile
     const uint32_t par = e >> 3;        // this warp takes the tiles with (step & 1) == par
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    // pair form: accumulator slots are released on the LEADER's barriers (the leader issues the MMAs)
+    const uint32_t tempty_rel0 = kPair ? mapa_shared(bar_tempty(0, h), 0) : bar_tempty(0, h);
+    const uint32_t tempty_rel1 = kPair ? mapa_shared(bar_tempty(1, h), 0) : bar_tempty(1, h);
     uint32_t step = 0, ucount = 1;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++ucount) {
-      const int seg = u / a.n_qblocks;
-      const int qb = u - seg * a.n_qblocks;
+    for (int u = unit0; u < total_units; u += unit_step, ++ucount) {
+      const int seg = u / a.n_qunits;
+      const int qu = u - seg * a.n_qunits;
+      const int qb = kPair ? qu * 2 + static_cast<int>(cta_rank) : qu;
       const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
       const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
       const int row = qb * kBlockQ + h * kTileM + quad * 32 + lane;
@@ -320,21 +386,23 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // query rows (and between the row's two threads): every holder of the row publishes its 2nd
       // best with atomicMin, everyone prunes with the minimum.  Any unit's 2nd best is an upper
       // bound of the row's final 2nd best, so this stays exact; without it every segment pays the
-      // ~2 ln(n) threshold-establishing updates again.
+      // ~2 ln(n) threshold-establishing updates again.  (row_thr is padded to whole query blocks; the
+      // phantom block of an odd pair lies past it and is never read or written.)
+      const bool thr_row = (kShare || kSeeded) && qb < a.n_qblocks;
       int* const gthr = (kShare || kSeeded) ? a.row_thr + (qb * kBlockQ + h * kTileM + quad * 32 + lane) : nullptr;
       int published = kNoKey;
-      int thr = (kShare || kSeeded) ? min(kNoKey, __ldcg(gthr)) : kNoKey;
+      int thr = thr_row ? min(kNoKey, __ldcg(gthr)) : kNoKey;
       for (int t = t0; t < t1; ++t, ++step) {
         if ((step & 1u) != par) continue;
         const uint32_t acc = step & 1u, bg = step % kBarGroups, bgph = (step / kBarGroups) & 1u;
-        const uint32_t slot = step % kCqSlots, cqph = (step / kCqSlots) & 1u;
+        const uint32_t slot = step % kCqS, cqph = (step / kCqS) & 1u;
         mbar_wait(bar_cqfull(slot), cqph);  // landed long ago: returns at the first poll
         mbar_wait(bar_tfull(bg, h), bgph);
         tc_fence_after();
-        const int32_t* cs = reinterpret_cast<const int32_t*>(smem + kOffCq + slot * kCqTileBytes);
+        const int32_t* cs = reinterpret_cast<const int32_t*>(smem + L::kOffCq + slot * kCqTileBytes);
         const int32_t* perm_s = cs + kCqPerm;
         // fetched now, folded in after this tile: the L2 round trip hides behind the tile's work
-        const int g_next = kShare ? __ldcg(gthr) : kNoKey;
+        const int g_next = (kShare && thr_row) ? __ldcg(gthr) : kNoKey;
         const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
         const int4* c4 = reinterpret_cast<const int4*>(cs);
         const int4 cmin = c4[kTileN / 4];
@@ -345,10 +413,13 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tmem_ld64_wait(taddr + 2 * kChunk, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(bg, h));
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_cluster(bg ? tempty_rel1 : tempty_rel0);
+          else mbar_arrive(bg ? tempty_rel1 : tempty_rel0);
+        }
         top2_chunk(v, c4 + 16, cmin.z, perm_s, a.idx_base, best, thr);
         top2_chunk(v + kChunk, c4 + 24, cmin.w, perm_s, a.idx_base, best, thr);
-        if (kShare) {
+        if (kShare && thr_row) {
           if (best.d2 < published) {
             published = best.d2;
             atomicMin(gthr, published);
@@ -356,7 +427,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
           thr = min(thr, g_next);
         }
       }
-      if (kSeeded && best.d2 < kNoKey) atomicMin(gthr, best.d2);
+      if (kSeeded && thr_row && best.d2 < kNoKey) atomicMin(gthr, best.d2);
       if (row < a.nq) {
         const int qn = a.qn[row];
         const int64_t o = ((static_cast<int64_t>(seg) * kParity + par) * a.nq + row) * 2;
@@ -370,8 +441,13 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (kPair) {
+    cluster_sync_all();  // the peer's shared memory and barriers stay alive until both CTAs are done
+    if (warp == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,21 +668,24 @@ __global__ void top2_from_keys_kernel(const longlong2* __restrict__ keys, int64_
 }
 
 struct Plan {
-  int n_tiles, n_qblocks, n_seg, grid;
+  int n_tiles, n_qblocks, n_qunits, n_seg, grid;
 };
 
 // Split every query block's database sweep into n_seg contiguous segments so that
-// n_qblocks*n_seg units fill the persistent grid evenly (cost = makespan in tile steps).
-Plan make_plan(int64_t nq, int64_t ndb, int sms) {
+// n_qunits*n_seg units fill the persistent grid evenly (cost = makespan in tile steps).  pair: a unit is
+// swept by a CTA pair (two query blocks side by side), the grid holds sms / 2 pairs.
+Plan make_plan(int64_t nq, int64_t ndb, int sms, bool pair = false) {
   Plan p;
   p.n_tiles = static_cast<int>((ndb + kTileN - 1) / kTileN);
   p.n_qblocks = static_cast<int>((nq + kBlockQ - 1) / kBlockQ);
+  p.n_qunits = pair ? (p.n_qblocks + 1) / 2 : p.n_qblocks;
+  if (pair) sms /= 2;
   p.n_seg = 1;
   if (p.n_tiles > 0 && p.n_qblocks > 0) {
     const int max_seg = p.n_tiles < 512 ? p.n_tiles : 512;
     int64_t best = -1;
     for (int s = 1; s <= max_seg; ++s) {
-      const int64_t units = static_cast<int64_t>(p.n_qblocks) * s;
+      const int64_t units = static_cast<int64_t>(p.n_qunits) * s;
       const int64_t waves = (units + sms - 1) / sms;
       // +12: pipeline fill and the slow-path chunks of a unit's first columns (measured; units of one
       // query block share their thresholds, so a later segment does not start from scratch)
@@ -617,15 +696,27 @@ Plan make_plan(int64_t nq, int64_t ndb, int sms) {
       }
     }
   }
-  const int64_t units = static_cast<int64_t>(p.n_qblocks) * p.n_seg;
-  p.grid = static_cast<int>(units < sms ? units : sms);
+  const int64_t units = static_cast<int64_t>(p.n_qunits) * p.n_seg;
+  p.grid = static_cast<int>(units < sms ? units : sms) * (pair ? 2 : 1);
   return p;
 }
 
-// [n_rows,128] u8 row-major, boxes of 128 rows x 128 B, 128-byte swizzle, OOB rows read as zero.
-int make_desc_map(CUtensorMap* m, const uint8_t* ptr, int64_t n_rows) {
+// [n_rows,128] u8 row-major, boxes of box_rows x 128 B, 128-byte swizzle, OOB rows read as zero.
+int make_desc_map(CUtensorMap* m, const uint8_t* ptr, int64_t n_rows, int box_rows = kTileN) {
   return make_rowmajor_map(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ptr, n_rows, SOD_DESC_DIM, SOD_DESC_DIM,
-                           kTileN);
+                           box_rows);
+}
+
+// Which form of the matcher sod_match_top2* launches: 0 = one CTA per SM (tcgen05.mma.cta_group::1),
+// 1 = CTA pairs (cta_group::2).  Process-wide; sod_set_option("match_cta_pair", v) or the environment
+// variable SOD_MATCH_CTA_PAIR at the first launch.
+int g_match_pair = -1;
+bool match_pair_enabled() {
+  if (g_match_pair < 0) {
+    const char* e = getenv("SOD_MATCH_CTA_PAIR");
+    g_match_pair = e ? (atoi(e) != 0) : SOD_MATCH_CTA_PAIR_DEFAULT;
+  }
+  return g_match_pair != 0;
 }
 
 }  // namespace
@@ -714,8 +805,26 @@ int64_t sod_row_thr_ints(int64_t n_query) {
 size_t sod_match_workspace_bytes(int64_t n_query, int64_t n_db) {
   if (n_query <= 0 || n_db <= 0) return 16;
   const int sms = device_sm_count();
-  const Plan p = make_plan(n_query, n_db, sms > 0 ? sms : 148);
-  return match_workspace_need(p, n_query) + 16;
+  // enough for either form of the kernel: the option may change between this query and the launch
+  const size_t single = match_workspace_need(make_plan(n_query, n_db, sms > 0 ? sms : 148, false), n_query);
+  const size_t pair = match_workspace_need(make_plan(n_query, n_db, sms > 0 ? sms : 148, true), n_query);
+  return (single > pair ? single : pair) + 16;
+}
+
+int sod_set_option(const char* name, int32_t value) {
+  SOD_CHECK_ARG(name, "null option name");
+  if (strcmp(name, "match_cta_pair") == 0) {
+    g_match_pair = value != 0;
+    return SOD_OK;
+  }
+  set_error("unknown option '%s'", name);
+  return SOD_ERR_INVALID_ARGUMENT;
+}
+
+int32_t sod_get_option(const char* name) {
+  if (name && strcmp(name, "match_cta_pair") == 0) return match_pair_enabled() ? 1 : 0;
+  set_error("unknown option '%s'", name ? name : "(null)");
+  return SOD_ERR_INVALID_ARGUMENT;
 }
 
 int sod_match_top2(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
@@ -756,14 +865,16 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
                 "q, db, cq and workspace must be 16-byte aligned");
   const int sms = device_sm_count();
   if (sms <= 0) return SOD_ERR_CUDA;
-  const Plan p = make_plan(n_query, (tile_end - tile_begin) * kTileN, sms);
+  const bool pair = match_pair_enabled() && sms >= 2;
+  const Plan p = make_plan(n_query, (tile_end - tile_begin) * kTileN, sms, pair);
   const size_t need = match_workspace_need(p, n_query);
   SOD_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
 
   CUtensorMap map_q, map_db;
   int rc = make_desc_map(&map_q, q, n_query);
   if (rc != SOD_OK) return rc;
-  rc = make_desc_map(&map_db, db, (n_db + kTileN - 1) / kTileN * kTileN);  // stored padded to whole tiles
+  // stored padded to whole tiles; a CTA of a pair stages half a tile (64 rows) per step
+  rc = make_desc_map(&map_db, db, (n_db + kTileN - 1) / kTileN * kTileN, pair ? kTileN / 2 : kTileN);
   if (rc != SOD_OK) return rc;
 
   MatchArgs a;
@@ -783,16 +894,33 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
   a.n_tiles = p.n_tiles;
   a.tile_begin = static_cast<int>(tile_begin);
   a.n_qblocks = p.n_qblocks;
+  a.n_qunits = p.n_qunits;
   a.n_seg = p.n_seg;
   a.idx_base = db_index_base;
 
   // The attribute is per device (a process may drive several), so it is set at every launch: ~1 us.
-  auto* kernel = a.row_thr ? match_top2_kernel<true> : match_top2_kernel<false>;
-  if (row_thr && p.n_seg == 1) kernel = match_top2_kernel<false, true>;
-  SOD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const bool seeded = row_thr && p.n_seg == 1, share = a.row_thr && !seeded;
+  auto* kernel = pair ? (seeded ? match_top2_kernel<false, true, true>
+                                : share ? match_top2_kernel<true, false, true> : match_top2_kernel<false, false, true>)
+                      : (seeded ? match_top2_kernel<false, true, false>
+                                : share ? match_top2_kernel<true, false, false> : match_top2_kernel<false, false, false>);
+  const int smem_bytes = pair ? Layout<true>::kSmemBytes : Layout<false>::kSmemBytes;
+  SOD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   {
     StageScope timed(SOD_STAGE_MATCH, st);
-    kernel<<<p.grid, kThreads, kSmemBytes, st>>>(map_q, map_db, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(p.grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    SOD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, map_q, map_db, a));
   }
   SOD_CHECK_LAUNCH("match_top2_kernel");
   top2_merge_kernel<<<mblocks, mthreads, 0, st>>>(a.part_idx, a.part_d2, p.n_seg * kParity, n_query,

@@ -10,6 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
 sys.path.insert(0, str(ROOT / "tests"))
 import scenes  # noqa: E402
+from sod_b200 import _capi  # noqa: E402
 from sod_b200 import engine as E  # noqa: E402
 
 
@@ -28,6 +29,7 @@ def main(n_objects=500, per_object=4000, iters=10):
     torch.cuda.synchronize()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     th, ta = [], []
+    _capi.timing_enable(True)
     for _ in range(iters):
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
@@ -38,6 +40,9 @@ def main(n_objects=500, per_object=4000, iters=10):
         torch.cuda.synchronize()
         th.append(e0.elapsed_time(e1))
         ta.append(e1.elapsed_time(e2))
+    stages = {k: _capi.timing_read(k) for k in _capi.STAGES}
+    _capi.timing_enable(False)
+    print("stage medians (ms): " + "  ".join(f"{k} {np.median(v):.3f}" for k, v in stages.items() if v))
     c = res.counters.cpu().numpy()
     a = aff.host(int(c[1]))
     hm, am = float(np.median(th)), float(np.median(ta))
