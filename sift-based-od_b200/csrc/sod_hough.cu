@@ -274,6 +274,7 @@ struct VoteArgs {
   const int32_t* grouped;    // match ids grouped by Hough space
   const uint32_t* base_bin;  // base bins in the same (grouped) order
   uint32_t* rank;            // per grouped position 16 slots: arrival rank of each of its votes in its bin
+  uint16_t* creator;         // per grouped position: which of the 16 votes created (took rank 0 of) its bin
   int64_t n_groups;
   Bins4 bins;
   int group_chunk;           // Hough spaces per ticket: 1 for few large spaces ... kGroupChunk for many sparse ones
@@ -299,29 +300,41 @@ __device__ __forceinline__ void for_each_vote(uint32_t base, const Bins4& bins, 
   }
 }
 
-// One Hough space: the four phases over the matches [beg, end) of the space.  Rank is the element type
-// of the per-vote arrival ranks (uint16_t while the space has at most 65,535 matches: half the traffic).
-//  A  every vote takes the next rank of its bin: ONE shared-memory atomic per vote; rank 0 created the bin
+// One Hough space: the four phases over the matches [beg, end) of the space.  kWide: arrival ranks as
+// 32-bit values (spaces of more than 65,535 matches), else packed 16-bit pairs (half the traffic).
+//  A  every vote takes the next rank of its bin: ONE shared-memory atomic per vote; rank 0 created the bin.
+//     The 16 ranks of a match stay in registers and leave as two (four) 16-byte stores, the creator bits
+//     as one 16-bit mask.
 //  B  the creating vote emits the bin record and turns the counter into the bin's offset
 //  C  every vote stores its match id at offset + rank: no atomic, the ranks of phase A are a permutation
 //  D  creators clear their counters for the next space
-template <typename Rank>
+template <bool kWide>
 __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, int64_t g, int beg, int end,
                                            int* s_counts) {
   // s_counts: [0] n_bins, [1] n_votes, [2] rec_base, [3] vote_base, [4] rec_cur, [5] vote_cur, [6] ok
+  constexpr int kWords = kWide ? 16 : 8;  // 32-bit words of rank storage per match
   const Bins4 bins = a.bins;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) s_counts[0] = s_counts[1] = s_counts[4] = s_counts[5] = 0;
   __syncthreads();
   int my_bins = 0, my_votes = 0;
   for (int p = beg + tid; p < end; p += kVoteThreads) {
-    Rank* rk = reinterpret_cast<Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+    uint32_t rk[kWords];
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) rk[i] = 0u;
+    unsigned created = 0;
     for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
       const uint32_t r = atomicAdd(&hist[code], 1u);
-      rk[o] = static_cast<Rank>(r);
-      my_bins += r == 0u;
+      if (kWide) rk[o] = r;
+      else rk[o >> 1] |= r << ((o & 1) * 16);
+      created |= (r == 0u ? 1u : 0u) << o;
       ++my_votes;
     });
+    uint4* dst = reinterpret_cast<uint4*>(a.rank + static_cast<int64_t>(p) * 16);
+#pragma unroll
+    for (int i = 0; i < kWords / 4; ++i) dst[i] = make_uint4(rk[4 * i], rk[4 * i + 1], rk[4 * i + 2], rk[4 * i + 3]);
+    a.creator[p] = static_cast<uint16_t>(created);
+    my_bins += __popc(created);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -345,9 +358,10 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
   const int rec_base = s_counts[2], vote_base = s_counts[3];
   if (ok) {
     for (int p = beg + tid; p < end; p += kVoteThreads) {
-      const Rank* rk = reinterpret_cast<const Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+      const unsigned created = a.creator[p];
+      if (!created) continue;
       for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
-        if (rk[o] != 0) return;
+        if (!(created >> o & 1u)) return;
         const int cnt = static_cast<int>(hist[code]);
         const int rec = rec_base + atomicAdd(&s_counts[4], 1);
         const int off = vote_base + atomicAdd(&s_counts[5], cnt);
@@ -363,15 +377,25 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
   if (ok) {
     for (int p = beg + tid; p < end; p += kVoteThreads) {
       const int m = a.grouped[p];
-      const Rank* rk = reinterpret_cast<const Rank*>(a.rank + static_cast<int64_t>(p) * 16);
-      for_each_vote(a.base_bin[p], bins, [&](int o, int code) { a.members_raw[hist[code] + rk[o]] = m; });
+      const uint4* src = reinterpret_cast<const uint4*>(a.rank + static_cast<int64_t>(p) * 16);
+      uint32_t rk[kWords];
+#pragma unroll
+      for (int i = 0; i < kWords / 4; ++i) {
+        const uint4 v = src[i];
+        rk[4 * i] = v.x; rk[4 * i + 1] = v.y; rk[4 * i + 2] = v.z; rk[4 * i + 3] = v.w;
+      }
+      for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
+        const uint32_t r = kWide ? rk[o] : (rk[o >> 1] >> ((o & 1) * 16)) & 0xFFFFu;
+        a.members_raw[hist[code] + r] = m;
+      });
     }
   }
   __syncthreads();
   for (int p = beg + tid; p < end; p += kVoteThreads) {
-    const Rank* rk = reinterpret_cast<const Rank*>(a.rank + static_cast<int64_t>(p) * 16);
+    const unsigned created = a.creator[p];
+    if (!created) continue;
     for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
-      if (rk[o] == 0) hist[code] = 0u;
+      if (created >> o & 1u) hist[code] = 0u;
     });
   }
   __syncthreads();
@@ -405,9 +429,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
       const int64_t g = gbase + s_list[li];
       const int beg = a.group_off[g], end = a.group_off[g + 1];
       if (end - beg <= 65535)
-        vote_space<uint16_t>(a, hist, g, beg, end, s_counts);
+        vote_space<false>(a, hist, g, beg, end, s_counts);
       else
-        vote_space<uint32_t>(a, hist, g, beg, end, s_counts);
+        vote_space<true>(a, hist, g, beg, end, s_counts);
     }
     __syncthreads();  // s_list / s_chunk are rewritten by the next ticket
   }
@@ -712,6 +736,7 @@ size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 struct HoughWs {
   int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket, *big_list, *huge_list;
   uint32_t *grouped_base, *rank;
+  uint16_t* creator;
   double* match_size;
   int64_t big_cap;
   size_t bytes;
@@ -733,6 +758,7 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.grouped = static_cast<int32_t*>(take(m * 4));
   w.grouped_base = static_cast<uint32_t*>(take(m * 4));
   w.rank = static_cast<uint32_t*>(take(m * 16 * 4));
+  w.creator = static_cast<uint16_t*>(take(m * 2));
   w.match_size = static_cast<double*>(take(m * 2 * 8));
   w.members_raw = static_cast<int32_t*>(take(cap_votes * 4));
   w.big_cap = cap_votes / (kSmallBin + 1) + 1;
@@ -891,7 +917,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   stage_end(SOD_STAGE_HOUGH_PREP, st);
 
   VoteArgs va;
-  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.rank = w.rank;
+  va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.rank = w.rank; va.creator = w.creator;
   va.n_groups = n_groups; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
