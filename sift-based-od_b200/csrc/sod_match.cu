@@ -39,7 +39,7 @@ namespace sod {
 namespace {
 
 #ifndef SOD_MATCH_CTA_PAIR_DEFAULT
-#define SOD_MATCH_CTA_PAIR_DEFAULT 0
+#define SOD_MATCH_CTA_PAIR_DEFAULT 1
 #endif
 
 constexpr int kTileM = 128;                 // query rows per MMA (TMEM lanes)

@@ -24,6 +24,28 @@ def run(nq, ndb, iters=10, kind="uniform"):
     if kind == "uniform":
         q = torch.randint(0, 256, (nq, 128), dtype=torch.uint8, device="cuda", generator=g)
         db = torch.randint(0, 256, (ndb, 128), dtype=torch.uint8, device="cuda", generator=g)
+    elif kind == "selfmatch":
+        # hostile leg 1: EVERY query is a database row + integer noise (100 % true matches)
+        db = sift_like_gpu(ndb, g)
+        src = torch.randint(0, ndb, (nq,), device="cuda", generator=g)
+        noise = torch.randint(-3, 4, (nq, 128), device="cuda", generator=g, dtype=torch.int16)
+        q = (db[src].to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+    elif kind == "cluster":
+        # hostile leg 2: dense near-duplicates - 1024 clusters of ndb/1024 rows within +-2 of their centre,
+        # queries = centres + noise: hundreds of database rows sit at almost the distance of the 2nd best
+        centres = sift_like_gpu(1024, g)
+        lab = torch.randint(0, 1024, (ndb,), device="cuda", generator=g)
+        db = (centres[lab].to(torch.int16) + torch.randint(-2, 3, (ndb, 128), device="cuda", generator=g,
+                                                            dtype=torch.int16)).clamp_(0, 255).to(torch.uint8)
+        ql = torch.randint(0, 1024, (nq,), device="cuda", generator=g)
+        q = (centres[ql].to(torch.int16) + torch.randint(-2, 3, (nq, 128), device="cuda", generator=g,
+                                                          dtype=torch.int16)).clamp_(0, 255).to(torch.uint8)
+    elif kind == "dup":
+        # the floor: ONE descriptor repeated ndb times and every query equal to it - every distance is 0, every
+        # chunk ties with the threshold and takes the exact path, the lowest indices win one tile at a time
+        row = sift_like_gpu(1, g)
+        db = row.expand(ndb, 128).contiguous()
+        q = row.expand(nq, 128).contiguous()
     elif kind == "noevent":
         # all-zero queries + two all-zero database rows (smallest norm -> first tile): the threshold is 0
         # after the first tile and nothing passes the bound any more: the shipped binary without updates
@@ -69,9 +91,13 @@ def run_float(nq, ndb, split, iters=10):
 
 if __name__ == "__main__":
     shapes = [(10000, 100000), (10000, 1000000), (65536, 1000000)]
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] != "--adversarial":
         shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
     kinds = os.environ.get("SOD_BENCH_KINDS", "uniform,sift").split(",")
+    if "--adversarial" in sys.argv:     # the hostile-data legs beside the friendly one
+        sys.argv.remove("--adversarial")
+        kinds = ["sift", "selfmatch", "cluster", "dup"]
+        shapes = [(65536, 1000000)]
     for kind in kinds:
         for nq, ndb in shapes:
             if kind in ("bf16", "bf16x3"):
