@@ -341,6 +341,13 @@ int sod_affine_verify(const sod_scene* scene, const int32_t* match_q, const int3
                       int32_t affine_threshold, double factor_x, double factor_y, int32_t max_passes,
                       const sod_affine_out* out, sod_stream_t stream);
 
+/* The Hough records (space, bin code, insertion-order key, six running means) of the bins listed in
+ * affine->valid_bin, in that order: out_* hold affine->cap_valid entries, the first counters[0] are written.
+ * What Main.post_process (main.py:159-168) reads of the surviving bins, gathered on the device so that the
+ * caller's read-back is plain copies. */
+int sod_valid_bin_records(const sod_hough_out* hough, const sod_affine_out* affine, int32_t* out_group,
+                          int32_t* out_code, int64_t* out_order, double* out_mean, sod_stream_t stream);
+
 /* remove_outliers' decision for caller-supplied parameters (AffineParameters.py:128-155):
  * keep[i] = !(|m1 x + m2 y + tx - u| > x_ref || |m3 x + m4 y + ty - v| > y_ref), params on the device. */
 int sod_affine_residual_keep(const float* model_xy, const float* query_xy, int64_t n,

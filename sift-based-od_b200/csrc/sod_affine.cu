@@ -282,6 +282,27 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
   }
 }
 
+// The Hough records of the bins that entered the affine stage, in the order of sod_affine_out.valid_bin:
+// what a caller reads back next to params / votes / status (one coalesced copy instead of four gathers).
+__global__ void valid_records_kernel(const int32_t* __restrict__ counters, const int32_t* __restrict__ valid_bin,
+                                     int64_t cap_valid, const int32_t* __restrict__ bin_group,
+                                     const int32_t* __restrict__ bin_code, const int64_t* __restrict__ bin_order,
+                                     const double* __restrict__ bin_mean, int32_t* __restrict__ out_group,
+                                     int32_t* __restrict__ out_code, int64_t* __restrict__ out_order,
+                                     double* __restrict__ out_mean) {
+  int64_t n = counters[0];
+  if (n > cap_valid) n = cap_valid;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < n;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int rec = valid_bin[v];
+    out_group[v] = bin_group[rec];
+    out_code[v] = bin_code[rec];
+    out_order[v] = bin_order[rec];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out_mean[v * 6 + c] = bin_mean[static_cast<int64_t>(rec) * 6 + c];
+  }
+}
+
 // remove_outliers with caller-supplied parameters (AffineParameters.py:128-155).
 __global__ void affine_residual_kernel(const float2* __restrict__ mxy, const float2* __restrict__ qxy,
                                        int64_t n, const double* __restrict__ p, double x_ref,
@@ -298,6 +319,22 @@ __global__ void affine_residual_kernel(const float2* __restrict__ mxy, const flo
 }  // namespace sod
 
 using namespace sod;
+
+extern "C" int sod_valid_bin_records(const sod_hough_out* hough, const sod_affine_out* affine, int32_t* out_group,
+                                     int32_t* out_code, int64_t* out_order, double* out_mean,
+                                     sod_stream_t stream) {
+  SOD_CHECK_ARG(hough && affine && out_group && out_code && out_order && out_mean, "null pointer");
+  SOD_CHECK_ARG(affine->counters && affine->valid_bin && hough->bin_group && hough->bin_code && hough->bin_order &&
+                    hough->bin_mean,
+                "null input array");
+  const int sms = device_sm_count();
+  if (sms <= 0) return SOD_ERR_CUDA;
+  valid_records_kernel<<<sms * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      affine->counters, affine->valid_bin, affine->cap_valid, hough->bin_group, hough->bin_code, hough->bin_order,
+      hough->bin_mean, out_group, out_code, out_order, out_mean);
+  SOD_CHECK_LAUNCH("valid_records_kernel");
+  return SOD_OK;
+}
 
 extern "C" int sod_affine_residual_keep(const float* model_xy, const float* query_xy, int64_t n,
                                         const double* params, double x_ref, double y_ref,

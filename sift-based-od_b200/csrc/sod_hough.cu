@@ -88,6 +88,7 @@ struct PoseArgs {
   int32_t* counters;
   int32_t* group_of;
   int32_t* group_count;
+  int32_t* group_rank;  // [M] arrival rank of the match inside its Hough space (the counting sort's position)
   double* match_size;  // [M][2] (w, h) of the match's model image, or nullptr: read again by the finish kernels
 };
 
@@ -119,7 +120,8 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
                                     static_cast<double>(a.sc.model.angle[ti])), kDegToRad);
     al = fmod(__dadd_rn(al, kTwoPi), kTwoPi);  // operand is > 0: Python's % equals fmod here
     if (al < 0.0) al = __dadd_rn(al, kTwoPi);
-    const double ca = cos(al), sa = sin(al);
+    double sa, ca;
+    sincos(al, &sa, &ca);
     const double qx = static_cast<double>(qp.x), qy = static_cast<double>(qp.y);
     const double bx = static_cast<double>(bins.x), by = static_cast<double>(bins.y);
     const XyBins c = xy_bins(ca, sa, tx, ty, qx, qy, bx, by, W, H);
@@ -162,7 +164,7 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
     }
     if (a.group_of) {
       a.group_of[i] = grp;
-      atomicAdd(&a.group_count[grp], 1);
+      a.group_rank[i] = atomicAdd(&a.group_count[grp], 1);
     }
   }
 }
@@ -256,14 +258,16 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
 }
 
 // Counting-sort scatter: match id and its base bin travel together, so that the voting kernel reads
-// both with coalesced loads instead of gathering base_bin[grouped[p]] in each of its four phases.
-__global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const uint32_t* __restrict__ base_bin,
-                                     const int32_t* n_dev, int64_t n_cap, int32_t* __restrict__ cursor,
-                                     int32_t* __restrict__ grouped, uint32_t* __restrict__ grouped_base) {
+// both with coalesced loads instead of gathering base_bin[grouped[p]] in each of its four phases.  The
+// position inside the space is the rank the pose kernel's counting atomic returned: no second atomic.
+__global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const int32_t* __restrict__ group_rank,
+                                     const uint32_t* __restrict__ base_bin, const int32_t* n_dev, int64_t n_cap,
+                                     const int32_t* __restrict__ group_off, int32_t* __restrict__ grouped,
+                                     uint32_t* __restrict__ grouped_base) {
   const int64_t n = live_count(n_dev, n_cap);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int pos = atomicAdd(&cursor[group_of[i]], 1);
+    const int pos = group_off[group_of[i]] + group_rank[i];
     grouped[pos] = static_cast<int32_t>(i);
     grouped_base[pos] = base_bin[i];
   }
@@ -486,8 +490,17 @@ __device__ __forceinline__ Member6 load_member(const FinishArgs& a, int m) {
   return Member6{{p0.x, p0.y, p1.x, p1.y, sz.x, sz.y}};
 }
 // PoseBin.update_* (PoseBin.py:19-43): mean <- (mean * votes + new) / (votes + 1), votes = j members so far.
-__device__ __forceinline__ double running_mean(double mean, double v, int j) {
-  return __ddiv_rn(__dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v), static_cast<double>(j + 1));
+// The six means of a bin divide by the same small integer, so the division is a correctly rounded
+// reciprocal (rcp = __drcp_rn(j + 1), once per member) followed by Markstein's sequence
+//   q = rn(a * rcp);  r = a - (j + 1) * q (exact in one FMA);  result = rn(q + r * rcp)
+// which returns the correctly rounded quotient rn(a / (j + 1)) for finite normal operands - the value IEEE
+// division gives (checked against exact rational arithmetic on 3e5 random operands) - at a
+// quarter of the instructions of six full divisions.
+__device__ __forceinline__ double running_mean(double mean, double v, int j, double rcp) {
+  const double a = __dadd_rn(__dmul_rn(mean, static_cast<double>(j)), v);
+  const double q = __dmul_rn(a, rcp);
+  const double r = __fma_rn(-static_cast<double>(j + 1), q, a);
+  return __fma_rn(r, rcp, q);
 }
 
 // One THREAD per bin (almost all bins hold a handful of votes): sort the members by match id (the
@@ -533,8 +546,9 @@ __global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const Fini
         const int m = s_m[j][t];
         a.members[off + j] = m;
         const Member6 v = load_member(a, m);
+        const double rcp = __drcp_rn(static_cast<double>(j + 1));
 #pragma unroll
-        for (int c = 0; c < 6; ++c) mean[c] = j == 0 ? v.v[c] : running_mean(mean[c], v.v[c], j);
+        for (int c = 0; c < 6; ++c) mean[c] = j == 0 ? v.v[c] : running_mean(mean[c], v.v[c], j, rcp);
       }
     }
 #pragma unroll
@@ -543,50 +557,72 @@ __global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const Fini
   }
 }
 
-// The sequential means of one sorted member list by one warp: 32 members are fetched at a time (one per
-// lane, all loads in flight together), then lanes 0..5 each advance one of the six recurrences with the
-// values handed over by shuffles - the dependent chain is the divide, not a memory access.
-__device__ __forceinline__ void warp_means(const FinishArgs& a, const int32_t* sorted, int cnt, int64_t rec, int lane) {
-  double mean = 0.0;
-  for (int base = 0; base < cnt; base += 32) {
-    const int n = min(32, cnt - base);
-    Member6 v;
-    if (lane < n) v = load_member(a, sorted[base + lane]);
-    else v = Member6{{0, 0, 0, 0, 0, 0}};
-    for (int j = 0; j < n; ++j) {
-      double x = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double vc = __shfl_sync(0xffffffffu, v.v[c], j);
-        if (lane == c) x = vc;
-      }
-      if (lane < 6) mean = (base + j) == 0 ? x : running_mean(mean, x, base + j);
-    }
-  }
-  if (lane < 6) a.bin_mean[rec * 6 + lane] = mean;
-  if (lane == 0) a.bin_order[rec] = order_key(a, rec, sorted[0]);
+// One component of one member: x, y, angle, scale from the pose row, w, h from the model image size.
+__device__ __forceinline__ double member_component(const FinishArgs& a, int m, int c) {
+  return c < 4 ? __ldg(a.pose + static_cast<int64_t>(m) * 4 + c) : __ldg(a.match_size + static_cast<int64_t>(m) * 2 + (c - 4));
 }
 
-// One warp per bin of 17 .. kWarpBin votes: rank-sort the members (ids are distinct), then the means.
-__global__ void hough_finish_big_kernel(const FinishArgs a) {
-  const int lane = threadIdx.x & 31;
+// The sequential means of sorted member lists by one warp: lane = (list k = lane / 6, component c = lane % 6),
+// five lists side by side (lanes 30, 31 idle).  Every lane runs ONE recurrence; the value of the next member is
+// fetched while the current step's dependent multiply / add / divide chain runs.
+__device__ __forceinline__ void warp_means5(const FinishArgs& a, const int32_t* const (&sorted)[5], const int (&cnt)[5],
+                                            const int64_t (&rec)[5], int lane) {
+  const int k = lane / 6, c = lane - k * 6;
+  const int32_t* mine = nullptr;
+  int n = 0;
+  int64_t my_rec = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    if (k == i) { mine = sorted[i]; n = cnt[i]; my_rec = rec[i]; }
+  if (k >= 5) n = 0;
+  double mean = 0.0;
+  double next = n > 0 ? member_component(a, mine[0], c) : 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double v = next;
+    if (j + 1 < n) next = member_component(a, mine[j + 1], c);
+    mean = j == 0 ? v : running_mean(mean, v, j, __drcp_rn(static_cast<double>(j + 1)));
+  }
+  if (n > 0) {
+    a.bin_mean[my_rec * 6 + c] = mean;
+    if (c == 0) a.bin_order[my_rec] = order_key(a, my_rec, mine[0]);
+  }
+}
+
+// Bins of 17 .. kWarpBin votes: a warp takes five of them; each is rank-sorted by the whole warp out of a
+// shared-memory copy (ids are distinct), then the five mean chains run side by side.
+constexpr int kBigWarps = 4;
+__global__ void __launch_bounds__(kBigWarps * 32) hough_finish_big_kernel(const FinishArgs a) {
+  __shared__ int32_t s_raw[kBigWarps][kWarpBin];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   int64_t n_big = a.list_count[0];
   if (n_big > a.big_cap) n_big = a.big_cap;
-  for (int64_t b = warp; b < n_big; b += n_warps) {
-    const int64_t rec = a.big_list[b];
-    const int off = a.bin_offset[rec], cnt = a.bin_count[rec];
-    const int32_t* raw = a.members_raw + off;
-    int32_t* out = a.members + off;
-    for (int i = lane; i < cnt; i += 32) {
-      const int32_t x = raw[i];
-      int rank = 0;
-      for (int j = 0; j < cnt; ++j) rank += raw[j] < x;
-      out[rank] = x;
+  for (int64_t b0 = warp * 5; b0 < n_big; b0 += n_warps * 5) {
+    const int32_t* sorted[5];
+    int cnt[5];
+    int64_t rec[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      sorted[i] = nullptr; cnt[i] = 0; rec[i] = 0;
+      if (b0 + i >= n_big) continue;
+      rec[i] = a.big_list[b0 + i];
+      const int off = a.bin_offset[rec[i]];
+      cnt[i] = a.bin_count[rec[i]];
+      const int32_t* raw = a.members_raw + off;
+      int32_t* out = a.members + off;
+      for (int j = lane; j < cnt[i]; j += 32) s_raw[w][j] = raw[j];
+      __syncwarp();
+      for (int j = lane; j < cnt[i]; j += 32) {
+        const int32_t x = s_raw[w][j];
+        int rank = 0;
+        for (int q = 0; q < cnt[i]; ++q) rank += s_raw[w][q] < x;
+        out[rank] = x;
+      }
+      __syncwarp();
+      sorted[i] = out;
     }
-    __syncwarp();
-    warp_means(a, out, cnt, rec, lane);
+    warp_means5(a, sorted, cnt, rec, lane);
   }
 }
 
@@ -672,7 +708,12 @@ __global__ void __launch_bounds__(kHugeThreads, 1) hough_finish_huge_kernel(cons
     }
     __threadfence_block();
     __syncthreads();
-    if (warp == 0) warp_means(a, out, cnt, rec, lane);
+    if (warp == 0) {
+      const int32_t* const sorted[5] = {out, nullptr, nullptr, nullptr, nullptr};
+      const int cnts[5] = {cnt, 0, 0, 0, 0};
+      const int64_t recs[5] = {rec, 0, 0, 0, 0};
+      warp_means5(a, sorted, cnts, recs, lane);
+    }
     __syncthreads();
   }
 }
@@ -734,7 +775,7 @@ compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict_
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
-  int32_t *group_of, *group_count, *group_off, *group_cursor, *grouped, *members_raw, *ticket, *big_list, *huge_list;
+  int32_t *group_of, *group_count, *group_off, *group_rank, *grouped, *members_raw, *ticket, *big_list, *huge_list;
   uint32_t *grouped_base, *rank;
   uint16_t* creator;
   double* match_size;
@@ -754,7 +795,7 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.group_of = static_cast<int32_t*>(take(m * 4));
   w.group_count = static_cast<int32_t*>(take((groups + 1) * 4));
   w.group_off = static_cast<int32_t*>(take((groups + 1) * 4));
-  w.group_cursor = static_cast<int32_t*>(take((groups + 1) * 4));
+  w.group_rank = static_cast<int32_t*>(take(m * 4));
   w.grouped = static_cast<int32_t*>(take(m * 4));
   w.grouped_base = static_cast<uint32_t*>(take(m * 4));
   w.rank = static_cast<uint32_t*>(take(m * 16 * 4));
@@ -821,7 +862,7 @@ int sod_estimate_pose(const sod_scene* scene, const int32_t* match_q, const int3
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = nullptr; pa.n_cap = n_matches;
   pa.bins = Bins4{bins, bins, bins, bins}; pa.sigma_lut = sigma_lut; pa.pose = pose; pa.base_bin = base_bin;
   pa.near_edge = near_edge; pa.counters = nullptr; pa.group_of = nullptr; pa.group_count = nullptr;
-  pa.match_size = nullptr;
+  pa.group_rank = nullptr; pa.match_size = nullptr;
   const int threads = 256;
   hough_pose_kernel<<<static_cast<unsigned>((n_matches + threads - 1) / threads), threads, 0,
                       static_cast<cudaStream_t>(stream)>>>(pa);
@@ -902,17 +943,17 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = n_matches_dev; pa.n_cap = n_matches;
   pa.bins = bins; pa.sigma_lut = sigma_lut; pa.pose = out->pose; pa.base_bin = out->base_bin;
   pa.near_edge = out->near_edge; pa.counters = out->counters; pa.group_of = w.group_of;
-  pa.group_count = w.group_count; pa.match_size = w.match_size;
+  pa.group_count = w.group_count; pa.group_rank = w.group_rank; pa.match_size = w.match_size;
   const int threads = 256;
   int64_t blocks = (n_matches + threads - 1) / threads;
   if (blocks > static_cast<int64_t>(sms) * 16) blocks = static_cast<int64_t>(sms) * 16;
   stage_begin(SOD_STAGE_HOUGH_PREP, st);
   hough_pose_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(pa);
   SOD_CHECK_LAUNCH("hough_pose_kernel");
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.group_count, n_groups, w.group_off, w.group_cursor, nullptr);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.group_count, n_groups, w.group_off, nullptr, nullptr);
   SOD_CHECK_LAUNCH("exclusive_scan_kernel");
   group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-      w.group_of, out->base_bin, n_matches_dev, n_matches, w.group_cursor, w.grouped, w.grouped_base);
+      w.group_of, w.group_rank, out->base_bin, n_matches_dev, n_matches, w.group_off, w.grouped, w.grouped_base);
   SOD_CHECK_LAUNCH("group_scatter_kernel");
   stage_end(SOD_STAGE_HOUGH_PREP, st);
 
@@ -946,7 +987,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   stage_begin(SOD_STAGE_HOUGH_FINISH, st);
   hough_finish_kernel<<<sms * 16, kFinishThreads, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_kernel");
-  hough_finish_big_kernel<<<sms * 8, 256, 0, st>>>(fa);
+  hough_finish_big_kernel<<<sms * 8, kBigWarps * 32, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_big_kernel");
   constexpr int kHugeSmem = kWindowWords * 4;
   SOD_CHECK_CUDA(cudaFuncSetAttribute(hough_finish_huge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHugeSmem));

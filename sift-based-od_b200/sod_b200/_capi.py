@@ -134,6 +134,7 @@ _PROTOS = {
                                  C.c_size_t, _p]),
     "sod_hough_vote_dims": (C.c_int, [C.POINTER(Scene), _p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32,
                                       C.POINTER(HoughOut), _p, C.c_size_t, _p]),
+    "sod_valid_bin_records": (C.c_int, [C.POINTER(HoughOut), C.POINTER(AffineOut), _p, _p, _p, _p, _p]),
     "sod_affine_verify": (C.c_int, [C.POINTER(Scene), _p, _p, C.POINTER(HoughOut), _i32, _i32, _i32,
                                     C.c_double, C.c_double, _i32, C.POINTER(AffineOut), _p]),
 }

@@ -455,10 +455,15 @@ class HoughVoter:
             self._res = HoughResult(int(m_cap), self.scene.n_groups, self.dims, self.scene.device)
         return self._res
 
+    def new_result(self, m_cap: int) -> HoughResult:
+        """A second output set of the same shape (callers that keep two steps in flight alternate them)."""
+        return HoughResult(int(m_cap), self.scene.n_groups, self.dims, self.scene.device)
+
     def vote(self, match_q: torch.Tensor, match_t: torch.Tensor, n_dev: torch.Tensor | None = None,
-             detail_min_count: int = 1) -> HoughResult:
+             detail_min_count: int = 1, result: HoughResult | None = None) -> HoughResult:
         """detail_min_count: bins with fewer votes get a record and a count but no sorted members,
-        means or order key (pass the vote threshold when only verified bins matter)."""
+        means or order key (pass the vote threshold when only verified bins matter).
+        result: write into this output set instead of the voter's own."""
         match_q = _require_cuda(match_q, torch.int32, "match_q")
         match_t = _require_cuda(match_t, torch.int32, "match_t")
         m = int(match_q.shape[0])
@@ -466,7 +471,9 @@ class HoughVoter:
         need = int(lib.sod_hough_workspace_bytes(m, sc.n_groups))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=sc.device)
-        res = self.reserve(m)
+        if result is not None and result.m_cap < m:
+            raise ValueError(f"HoughResult sized for {result.m_cap} matches cannot take {m}")
+        res = result if result is not None else self.reserve(m)
         s, o = sc.struct(), res.struct()
         check(lib.sod_hough_vote_dims(C.byref(s), _ptr(match_q), _ptr(match_t), m, _ptr(n_dev), *self.dims,
                                       _ptr(self.lut), int(detail_min_count), C.byref(o), _ptr(self._ws),
@@ -488,6 +495,22 @@ class AffineResult:
         self.votes = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
         self.status = torch.empty(self.cap_valid, dtype=torch.int32, device=device)
         self.member_keep = torch.empty(hough.cap_votes, dtype=torch.uint8, device=device)
+        self._records = None
+
+    def records(self, hough: "HoughResult"):
+        """(group, code, order, mean) of the bins in valid_bin, gathered on the device (sod_valid_bin_records);
+        the first counters[0] entries are meaningful."""
+        if self._records is None:
+            dev = self.valid_bin.device
+            self._records = (torch.empty(self.cap_valid, dtype=torch.int32, device=dev),
+                             torch.empty(self.cap_valid, dtype=torch.int32, device=dev),
+                             torch.empty(self.cap_valid, dtype=torch.int64, device=dev),
+                             torch.empty((self.cap_valid, 6), dtype=torch.float64, device=dev))
+        g, c, o, m = self._records
+        h, a = hough.struct(), self.struct()
+        check(lib.sod_valid_bin_records(C.byref(h), C.byref(a), _ptr(g), _ptr(c), _ptr(o), _ptr(m), _stream()),
+              "sod_valid_bin_records")
+        return self._records
 
     def struct(self) -> AffineOut:
         return AffineOut(_ptr(self.counters), _ptr(self.valid_bin), _ptr(self.params), _ptr(self.votes),

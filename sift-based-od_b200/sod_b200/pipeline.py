@@ -214,12 +214,16 @@ class DetectionPipeline:
         self.voter = E.HoughVoter(self.scene, bins)
         # Outputs of the Hough and affine stages are sized ONCE for max_queries: a later, larger batch
         # must never meet buffers that were sized for an earlier, smaller one.
-        self._hough = self.voter.reserve(self.max_queries)
-        self._aff = E.AffineResult(self._hough, self.vote_threshold, self.device)
+        # Two sets, alternating with the query-buffer set: detect_batches keeps step i+1 enqueued while the
+        # results of step i are read back.
+        self._hough = [self.voter.reserve(self.max_queries), None]
+        self._aff = [E.AffineResult(self._hough[0], self.vote_threshold, self.device), None]
         # two sets of query-side buffers: set 0 is the one allocated above; set 1 appears on first use
         self._qsets = [dict(des=self.q_des, xy=self.scene.q_xy, angle=self.scene.q_angle,
                             octave=self.scene.q_octave, frame=self.scene.q_frame), None]
         self._copy_stream = None
+        self._fetch_stream = None
+        self._pinned: dict = {}
         self._loaded = [None, None]      # event: the set's host->device copies have landed
         self._consumed = [None, None]    # event: the kernels that read the set have been enqueued and finished
         self.peer, self.peer_error = None, None
@@ -239,7 +243,7 @@ class DetectionPipeline:
         # our kernels per detect_device call; the key exchange of a database-sharded run is
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
-        self.launches_per_call = 17 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
+        self.launches_per_call = 18 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
             (3 + (3 if self.sweep_stages > 1 else 0) if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
@@ -395,14 +399,20 @@ class DetectionPipeline:
             idx, d2, dist_f, ok = merge(idx[None], d2[None])
         lo, hi = (self.row_lo, self.row_hi) if self.world > 1 else (0, 2 ** 31 - 1)
         mq, mt, n_dev = E.compact_matches(idx, ok, lo, hi)
-        hough = self.voter.vote(mq, mt, n_dev, detail_min_count=self.vote_threshold)
+        if self._hough[slot] is None:
+            self._hough[slot] = self.voter.new_result(self.max_queries)
+            self._aff[slot] = E.AffineResult(self._hough[slot], self.vote_threshold, self.device)
+        hough = self.voter.vote(mq, mt, n_dev, detail_min_count=self.vote_threshold, result=self._hough[slot])
         aff = E.affine_verify(self.scene, mq, mt, hough, self.vote_threshold, self.affine_threshold,
-                              result=self._aff)
+                              result=self._aff[slot])
+        records = aff.records(hough)        # what fetch() reads of the surviving bins, gathered on the device
+        counters = torch.cat([n_dev, hough.counters, aff.counters])
+        done = None
         if _events:
-            self._consumed[slot] = torch.cuda.Event()
-            self._consumed[slot].record()
+            self._consumed[slot] = done = torch.cuda.Event()
+            done.record()
         return dict(idx=idx, d2=d2, dist=dist_f, ok=ok, match_q=mq, match_t=mt, n_matches=n_dev,
-                    hough=hough, affine=aff, n=n)
+                    hough=hough, affine=aff, n=n, records=records, counters=counters, done=done)
 
     # ---------------------------------------------------------------- host in, host out
     def detect(self, des, xy, angle, octave, frame) -> dict:
@@ -412,47 +422,72 @@ class DetectionPipeline:
         return self.fetch(r)
 
     def detect_batches(self, batches):
-        """Host batches in, host results out, with the host->device copy of batch i+1 overlapping the
-        kernels of batch i (two query-buffer sets, one copy stream).  `batches` yields
-        (des, xy, angle, octave, frame) tuples of pinned host arrays; results are yielded in order."""
+        """Host batches in, host results out, pipelined one step deep: while the results of batch i are read
+        back, the kernels of batch i+1 are already enqueued (two query-buffer sets, two Hough / affine output
+        sets, one copy stream), so neither the host->device copy, nor the device->host read, nor the launch
+        overhead of a step leaves the GPU idle.  `batches` yields (des, xy, angle, octave, frame) tuples of
+        pinned host arrays; results are yielded in order."""
         it = iter(batches)
-        nxt = next(it, None)
         slot = 0
-        if nxt is not None:
-            n_next = self.load_queries(*nxt, slot=slot, overlap=True)
-        while nxt is not None:
-            r = self.detect_device(n_next, slot)
-            nxt = next(it, None)
-            if nxt is not None:
-                n_next = self.load_queries(*nxt, slot=slot ^ 1, overlap=True)
-            yield self.fetch(r)
+        pending = None
+        for batch in it:
+            n = self.load_queries(*batch, slot=slot, overlap=True)
+            r = self.detect_device(n, slot)
+            if pending is not None:
+                yield self.fetch(pending)
+            pending = r
             slot ^= 1
+        if pending is not None:
+            yield self.fetch(pending)
+
+    def _host_copy(self, name: str, src: torch.Tensor) -> np.ndarray:
+        """src -> a pinned staging buffer (grown on demand) on the fetch stream; the caller synchronises the
+        stream and copies the view out before the next fetch reuses the buffer."""
+        n = src.numel()
+        buf = self._pinned.get(name)
+        if buf is None or buf.numel() < n or buf.dtype != src.dtype:
+            buf = torch.empty(max(n, 1) * 2, dtype=src.dtype, pin_memory=True)
+            self._pinned[name] = buf
+        view = buf[:n].view(src.shape)
+        view.copy_(src, non_blocking=True)
+        return view.numpy()
 
     def fetch(self, r: dict) -> dict:
-        """Device -> host read of one result: matches, counters, verified bins of this rank."""
-        counters = torch.cat([r["n_matches"], r["hough"].counters, r["affine"].counters]).cpu().numpy()
-        n_m, n_bins, n_votes, n_edge, ovf, n_open = (int(v) for v in counters[:6])
-        n_valid, ovf2, n_singular, n_res_edge = (int(v) for v in counters[9:13])
-        if ovf or ovf2:
-            raise RuntimeError("output capacity exceeded")
-        a = r["affine"]
-        # after the exchange every rank holds the merged lists of ALL query rows; with result_rows="own"
-        # a rank reads back only the rows of its slice (the same rows it uploaded)
-        _, lo, hi = self.own_rows(r["n"]) if self.result_rows == "own" else (0, 0, r["n"])
-        out = dict(
-            idx=r["idx"][lo:hi].cpu().numpy(), ok=r["ok"][lo:hi].cpu().numpy(), row_lo=lo, n_matches=n_m, n_bins=n_bins,
-            n_votes=n_votes, n_near_edge=n_edge, n_unresolved_edge=n_open, n_valid=n_valid,
-            n_singular=n_singular, n_residual_edge=n_res_edge,
-            valid_bin=a.valid_bin[:n_valid].cpu().numpy(), params=a.params[:n_valid].cpu().numpy(),
-            votes=a.votes[:n_valid].cpu().numpy(), status=a.status[:n_valid].cpu().numpy())
-        h = r["hough"]
-        vb = a.valid_bin[:n_valid].long()
-        group = h.bin_group[vb].cpu().numpy()
-        out["valid_group"] = group if self._local_spaces == self.spaces_per_frame else \
-            global_space_ids(group, self._local_spaces, self.n_objects, self.obj_lo)
-        out["valid_code"] = h.bin_code[vb].cpu().numpy()
-        out["valid_order"] = h.bin_order[vb].cpu().numpy()
-        out["valid_mean"] = h.bin_mean[vb].cpu().numpy()
+        """Device -> host read of one result: matches, counters, verified bins of this rank.  Plain copies on
+        a stream of their own that only waits for the step that produced `r`: kernels of a later step that
+        are already enqueued (detect_batches) keep running underneath."""
+        if self._fetch_stream is None:
+            self._fetch_stream = torch.cuda.Stream(self.device)
+            self._pinned = {}
+        st = self._fetch_stream
+        st.wait_event(r["done"]) if r.get("done") is not None else st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            c_host = self._host_copy("counters", r["counters"])
+            st.synchronize()
+            n_m, n_bins, n_votes, n_edge, ovf, n_open = (int(v) for v in c_host[:6])
+            n_valid, ovf2, n_singular, n_res_edge = (int(v) for v in c_host[9:13])
+            if ovf or ovf2:
+                raise RuntimeError("output capacity exceeded")
+            a = r["affine"]
+            # after the exchange every rank holds the merged lists of ALL query rows; with result_rows="own"
+            # a rank reads back only the rows of its slice (the same rows it uploaded)
+            _, lo, hi = self.own_rows(r["n"]) if self.result_rows == "own" else (0, 0, r["n"])
+            g, code, order, mean = r["records"]
+            views = dict(idx=self._host_copy("idx", r["idx"][lo:hi]), ok=self._host_copy("ok", r["ok"][lo:hi]),
+                         valid_bin=self._host_copy("valid_bin", a.valid_bin[:n_valid]),
+                         params=self._host_copy("params", a.params[:n_valid]),
+                         votes=self._host_copy("votes", a.votes[:n_valid]),
+                         status=self._host_copy("status", a.status[:n_valid]),
+                         valid_group=self._host_copy("valid_group", g[:n_valid]),
+                         valid_code=self._host_copy("valid_code", code[:n_valid]),
+                         valid_order=self._host_copy("valid_order", order[:n_valid]),
+                         valid_mean=self._host_copy("valid_mean", mean[:n_valid]))
+            st.synchronize()
+        out = {k: v.copy() for k, v in views.items()}
+        out.update(row_lo=lo, n_matches=n_m, n_bins=n_bins, n_votes=n_votes, n_near_edge=n_edge,
+                   n_unresolved_edge=n_open, n_valid=n_valid, n_singular=n_singular, n_residual_edge=n_res_edge)
+        if self._local_spaces != self.spaces_per_frame:
+            out["valid_group"] = global_space_ids(out["valid_group"], self._local_spaces, self.n_objects, self.obj_lo)
         return out
 
     def final_poses(self, out: dict) -> dict[int, list]:
