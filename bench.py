@@ -662,7 +662,7 @@ def run_ours(args):
             pass
         traffic = None
         try:  # dram__bytes_read+write of one match_top2 launch, from the committed ncu --set full capture
-            tj = json.loads((ROOT / "profiles" / "r01_match_top2_traffic.json").read_text())
+            tj = json.loads((ROOT / "profiles" / "r02_match_top2_traffic.json").read_text())
             if world == 1 and (args.frames, args.per_frame, args.objects, args.kp_per_object) == (256, 5000, 1000, 1000):
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:

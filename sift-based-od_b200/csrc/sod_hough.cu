@@ -199,9 +199,9 @@ __global__ void pose_bin_index_kernel(const double* __restrict__ pose, int64_t n
                 (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
 }
 
-// Exclusive scan of n ints by one CTA, 8 consecutive elements per thread and round (n is the number
-// of Hough spaces or of compaction blocks: up to a few 100k, i.e. a few dozen rounds).
-constexpr int kScanItems = 8;
+// Exclusive scan of n ints by one CTA, 32 consecutive elements per thread and round (n is the number
+// of Hough spaces or of compaction blocks: up to a few 100k, i.e. a handful of rounds of 32,768).
+constexpr int kScanItems = 32;
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ in,
                                                               int64_t n, int32_t* __restrict__ out,
                                                               int32_t* __restrict__ out_copy,

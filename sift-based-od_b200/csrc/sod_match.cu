@@ -451,17 +451,24 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 (query side): one warp per descriptor row, 4 bytes per lane, __dp4a for the squares.
+// K1 (query side): eight threads per descriptor row, 16 bytes per thread (four rows per warp), __dp4a for
+// the squares, a three-step shuffle inside the group of eight.  Streaming: 128 B in, 4 B out per row.
 __global__ void row_sqnorm_kernel(const uint8_t* __restrict__ x, int64_t n_rows,
                                   int32_t* __restrict__ out) {
-  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const uint32_t w = reinterpret_cast<const uint32_t*>(x + row * SOD_DESC_DIM)[lane];
-  uint32_t s = __dp4a(w, w, 0u);
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = t >> 3;
+  const int part = threadIdx.x & 7;
+  uint32_t s = 0;
+  if (row < n_rows) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + row * SOD_DESC_DIM) + part);
+    s = __dp4a(w.x, w.x, s);
+    s = __dp4a(w.y, w.y, s);
+    s = __dp4a(w.z, w.z, s);
+    s = __dp4a(w.w, w.w, s);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[row] = static_cast<int32_t>(s);
+  for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (part == 0 && row < n_rows) out[row] = static_cast<int32_t>(s);
 }
 
 // K1 (database side), step 1: |t|^2 of every row as a sort key, row index as the value.
@@ -783,7 +790,7 @@ int sod_query_prepare(const uint8_t* q, int64_t n_rows, int32_t* qn, sod_stream_
   if (n_rows == 0) return SOD_OK;
   SOD_CHECK_ARG(q && qn, "null pointer");
   const int threads = 256;
-  const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
+  const int64_t blocks = (n_rows * 8 + threads - 1) / threads;
   row_sqnorm_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       q, n_rows, qn);
   SOD_CHECK_LAUNCH("row_sqnorm_kernel");
