@@ -130,6 +130,7 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
   for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < n_valid;
        v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int rec = a.out.valid_bin[v];
+    SOD_DCHECK(rec >= 0 && rec < a.cap_bins);
     const int cnt = a.bin_count[rec];
     if (cnt > kSmallAffine) continue;
     const int off = a.bin_offset[rec];
@@ -153,6 +154,8 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
       for (int j = 0; j < cnt; ++j) {
         if (!(alive >> j & 1u)) continue;
         const int m = mem[j];
+        SOD_DCHECK(m >= 0 && a.match_t[m] >= 0 && a.match_t[m] < a.sc.model.n && a.match_q[m] >= 0 &&
+                   a.match_q[m] < a.sc.query.n);
         const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
         const double x = pm.x, y = pm.y, u = pq.x, w = pq.y;
         sxx += x * x; sxy += x * y; sx += x; syy += y * y; sy += y; sn += 1.0;

@@ -7,6 +7,15 @@
 
 #include "../../include/sod.h"
 
+// Device-side bounds checks of every data-dependent index (compute-sanitizer is closed on the B200 pool):
+// compiled in with -DSOD_DEVICE_CHECKS (python -m sod_b200.build --variant checked -DSOD_DEVICE_CHECKS), a
+// violated check traps, i.e. the launch fails and the test that ran it reports a CUDA error.
+#ifdef SOD_DEVICE_CHECKS
+#define SOD_DCHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define SOD_DCHECK(cond) do { } while (0)
+#endif
+
 namespace sod {
 
 void set_error(const char* fmt, ...);

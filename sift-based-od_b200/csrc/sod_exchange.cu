@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) xchg_push_kernel(const XchgArgs a, const 
        row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const longlong2 k = top2_pack_keys(*reinterpret_cast<const int2*>(idx + row * 2),
                                        *reinterpret_cast<const uint2*>(d2 + row * 2));
+    SOD_DCHECK(row < a.max_query);
     for (int p = 0; p < a.world; ++p) key_slot(a.peer[p], parity, a.rank, a.world, a.max_query)[row] = k;
   }
   __threadfence_system();  // this thread's peer stores are visible system-wide before the block reports

@@ -104,12 +104,15 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int qi = a.match_q[i], ti = a.match_t[i];
+    SOD_DCHECK(qi >= 0 && qi < a.sc.query.n && ti >= 0 && ti < a.sc.model.n);
     const float2 qp = reinterpret_cast<const float2*>(a.sc.query.xy)[qi];
     const float2 mp = reinterpret_cast<const float2*>(a.sc.model.xy)[ti];
     const int frame = a.sc.query_frame ? a.sc.query_frame[qi] : 0;
     const double W = a.sc.frame_wh[2 * frame], H = a.sc.frame_wh[2 * frame + 1];
     const int img = a.sc.model_image[ti];
+    SOD_DCHECK(frame >= 0 && frame < a.sc.n_frames && img >= 0 && img < a.sc.n_images);
     const int grp = frame * a.sc.groups_per_frame + (a.sc.image_group ? a.sc.image_group[img] : 0);
+    SOD_DCHECK(grp >= 0 && grp < a.sc.n_frames * a.sc.groups_per_frame);
     const double cx = a.sc.image_centroid[2 * img], cy = a.sc.image_centroid[2 * img + 1];
     // scale_factor = m_scale / q_scale = 2^(q_octave - m_octave), exact
     const int k = sext8(a.sc.query.octave[qi]) - sext8(a.sc.model.octave[ti]);
@@ -268,6 +271,7 @@ __global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int pos = group_off[group_of[i]] + group_rank[i];
+    SOD_DCHECK(pos >= 0 && pos < n);
     grouped[pos] = static_cast<int32_t>(i);
     grouped_base[pos] = base_bin[i];
   }
@@ -328,7 +332,9 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
     for (int i = 0; i < kWords; ++i) rk[i] = 0u;
     unsigned created = 0;
     for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
+      SOD_DCHECK(code >= 0 && code < bins.total());
       const uint32_t r = atomicAdd(&hist[code], 1u);
+      SOD_DCHECK(kWide || r <= 0xFFFFu);
       if (kWide) rk[o] = r;
       else rk[o >> 1] |= r << ((o & 1) * 16);
       created |= (r == 0u ? 1u : 0u) << o;
@@ -369,6 +375,7 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
         const int cnt = static_cast<int>(hist[code]);
         const int rec = rec_base + atomicAdd(&s_counts[4], 1);
         const int off = vote_base + atomicAdd(&s_counts[5], cnt);
+        SOD_DCHECK(rec < a.cap_bins && static_cast<int64_t>(off) + cnt <= a.cap_votes);
         a.bin_group[rec] = static_cast<int32_t>(g);
         a.bin_code[rec] = code;
         a.bin_count[rec] = cnt;
@@ -390,6 +397,7 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
       }
       for_each_vote(a.base_bin[p], bins, [&](int o, int code) {
         const uint32_t r = kWide ? rk[o] : (rk[o >> 1] >> ((o & 1) * 16)) & 0xFFFFu;
+        SOD_DCHECK(static_cast<int64_t>(hist[code]) + r < a.cap_votes);
         a.members_raw[hist[code] + r] = m;
       });
     }
@@ -523,6 +531,7 @@ __global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const Fini
       continue;
     }
     const int off = a.bin_offset[rec];
+    SOD_DCHECK(off >= 0 && cnt >= 1);
     double mean[6];
     int first;
     if (cnt == 1) {
@@ -617,6 +626,7 @@ __global__ void __launch_bounds__(kBigWarps * 32) hough_finish_big_kernel(const 
         const int32_t x = s_raw[w][j];
         int rank = 0;
         for (int q = 0; q < cnt[i]; ++q) rank += s_raw[w][q] < x;
+        SOD_DCHECK(rank < cnt[i] && cnt[i] <= kWarpBin);
         out[rank] = x;
       }
       __syncwarp();
@@ -699,6 +709,7 @@ __global__ void __launch_bounds__(kHugeThreads, 1) hough_finish_huge_kernel(cons
         while (word) {
           const int bit = __ffs(word) - 1;
           word &= word - 1;
+          SOD_DCHECK(pos < cnt);
           out[pos++] = static_cast<int32_t>(w0 + (static_cast<int64_t>(tid * kPer + k) << 5) + bit);
         }
       }
@@ -767,6 +778,7 @@ compact_write_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict_
   __syncthreads();
   if (keep) {
     const int pos = block_off[blockIdx.x] + warp_base[warp] + __popc(b & ((1u << lane) - 1u));
+    SOD_DCHECK(pos >= 0 && pos < n);
     match_q[pos] = static_cast<int32_t>(i);
     match_t[pos] = t;
   }

@@ -169,6 +169,7 @@ __device__ __forceinline__ void top2_chunk(const uint32_t* v, const int4* __rest
   if (cmin - 2 * u2 <= thr) scan(18, 27);
   if (cmin - 2 * u3 <= thr) scan(27, 32);
   if ((t1 >> 8) > thr) return;
+  SOD_DCHECK((t1 & 0xFF) < kTileN && (t2 == INT_MAX || (t2 & 0xFF) < kTileN));
   const int o1 = perm_s[t1 & 0xFF];
   if (o1 >= 0) best.offer(t1 >> 8, idx_base + o1);
   thr = min(thr, best.d2);
@@ -431,6 +432,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (row < a.nq) {
         const int qn = a.qn[row];
         const int64_t o = ((static_cast<int64_t>(seg) * kParity + par) * a.nq + row) * 2;
+        SOD_DCHECK(seg < a.n_seg && (best.k1 == kNoKey64 || static_cast<int>(best.k1 & 0xFFFFFFFFll) >= a.idx_base));
         const int d1 = static_cast<int>(best.k1 >> 32), d2 = static_cast<int>(best.k2 >> 32);
         a.part_d2[o + 0] = d1 != kNoKey ? static_cast<uint32_t>(d1 + qn) : 0xFFFFFFFFu;
         a.part_d2[o + 1] = d2 != kNoKey ? static_cast<uint32_t>(d2 + qn) : 0xFFFFFFFFu;
