@@ -369,11 +369,24 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int e = warp - 4;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int h = (e >> 2) & 1;         // which query half-tile
-    const uint32_t par = e >> 3;        // this warp takes the tiles with (step & 1) == par
+    uint32_t par = e >> 3;              // this warp takes the tiles with (step & 1) == par
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    // Loop invariants the compiler would otherwise rebuild at the top of EVERY tile step from special
+    // registers (S2R SR_TID.X for the parity, S2R SR_CgaCtaId for the shared-memory window of a cluster
+    // launch - tens of cycles each, in front of the barrier waits): keep them in registers.
+    uint32_t tfull_h = bar_tfull(0, h);      // + 16 * (step % kBarGroups)
+    uint32_t cqfull_0 = bar_cqfull(0);       // + 8 * slot
+    uint32_t cq_0 = base + L::kOffCq;        // + slot * kCqTileBytes (shared-memory window address)
+    uint32_t taddr_h = tmem_base + lane_sel + h * kTileN;   // + (step & 1) * (kHalves * kTileN)
+    asm volatile("" : "+r"(par), "+r"(tfull_h), "+r"(cqfull_0), "+r"(cq_0), "+r"(taddr_h));
     // pair form: accumulator slots are released on the LEADER's barriers (the leader issues the MMAs)
-    const uint32_t tempty_rel0 = kPair ? mapa_shared(bar_tempty(0, h), 0) : bar_tempty(0, h);
-    const uint32_t tempty_rel1 = kPair ? mapa_shared(bar_tempty(1, h), 0) : bar_tempty(1, h);
+    uint32_t tempty_rel0 = kPair ? mapa_shared(bar_tempty(0, h), 0) : bar_tempty(0, h);
+    uint32_t tempty_rel1 = kPair ? mapa_shared(bar_tempty(1, h), 0) : bar_tempty(1, h);
+    if constexpr (kPair) {
+      // keep the two cluster addresses in registers: rematerialised, each release would re-read the cluster
+      // rank (S2R, tens of cycles) on the critical path between the TMEM load and the slot's release
+      asm volatile("" : "+r"(tempty_rel0), "+r"(tempty_rel1));
+    }
     uint32_t step = 0, ucount = 1;
     for (int u = unit0; u < total_units; u += unit_step, ++ucount) {
       const int seg = u / a.n_qunits;
@@ -397,14 +410,14 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if ((step & 1u) != par) continue;
         const uint32_t acc = step & 1u, bg = step % kBarGroups, bgph = (step / kBarGroups) & 1u;
         const uint32_t slot = step % kCqS, cqph = (step / kCqS) & 1u;
-        mbar_wait(bar_cqfull(slot), cqph);  // landed long ago: returns at the first poll
-        mbar_wait(bar_tfull(bg, h), bgph);
+        mbar_wait(cqfull_0 + 8u * slot, cqph);  // landed long ago: returns at the first poll
+        mbar_wait(tfull_h + 16u * bg, bgph);
         tc_fence_after();
-        const int32_t* cs = reinterpret_cast<const int32_t*>(smem + L::kOffCq + slot * kCqTileBytes);
+        const int32_t* cs = reinterpret_cast<const int32_t*>(__cvta_shared_to_generic(cq_0 + slot * kCqTileBytes));
         const int32_t* perm_s = cs + kCqPerm;
         // fetched now, folded in after this tile: the L2 round trip hides behind the tile's work
         const int g_next = (kShare && thr_row) ? __ldcg(gthr) : kNoKey;
-        const uint32_t taddr = tmem_base + lane_sel + acc * (kHalves * kTileN) + h * kTileN;
+        const uint32_t taddr = taddr_h + acc * (kHalves * kTileN);
         const int4* c4 = reinterpret_cast<const int4*>(cs);
         const int4 cmin = c4[kTileN / 4];
         uint32_t v[2 * kChunk];
