@@ -48,7 +48,6 @@ constexpr int kBlockQ = kTileM * kHalves;   // 256 query rows per unit
 constexpr int kTileN = SOD_TILE_ROWS;       // database rows per MMA
 constexpr int kTileBytes = kTileN * SOD_DESC_DIM;  // 16 KB (A half-tile has the same size)
 constexpr int kStages = 6;
-constexpr int kCqSlots = kStages + 6;       // see the slot-reuse argument in the producer
 constexpr int kChunk = 32;                  // accumulator columns per tcgen05.ld
 constexpr int kCqTile = SOD_CQ_TILE_INTS;   // 128 x |t|^2 + 4 per-chunk minima + 128 x original row
 constexpr int kCqPerm = kTileN + 4;         // offset of the permutation inside a tile's slice
@@ -77,7 +76,8 @@ template <bool kPair>
 struct Layout {
   static constexpr int kStagesL = kPair ? 8 : kStages;
   static constexpr int kBStageBytes = kPair ? kTileBytes / 2 : kTileBytes;
-  static constexpr int kCqSlotsL = kStagesL + 6;            // see the slot-reuse argument in the producer
+  static constexpr int kCqSlotsL = 16;                      // >= kStagesL + 3 (slot-reuse argument in the producer);
+                                                            // a power of two keeps `step % slots` a mask
   static constexpr int kOffA = 0;                                     // [2 buffers][2 halves][16 KB]
   static constexpr int kOffB = kOffA + 2 * kHalves * kTileBytes;      // [stages][16 KB | 8 KB]
   static constexpr int kOffCq = kOffB + kStagesL * kBStageBytes;      // [cq slots][260] int32
@@ -85,6 +85,7 @@ struct Layout {
   static constexpr int kNumBars = 2 * kStagesL + 4 + 4 * kBarGroups + kCqSlotsL;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;          // +1024: manual 1 KB alignment
+  static_assert(kCqSlotsL >= kStagesL + 3 && (kCqSlotsL & (kCqSlotsL - 1)) == 0, "cq ring too shallow");
 };
 
 struct MatchArgs {
@@ -378,7 +379,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint32_t cqfull_0 = bar_cqfull(0);       // + 8 * slot
     uint32_t cq_0 = base + L::kOffCq;        // + slot * kCqTileBytes (shared-memory window address)
     uint32_t taddr_h = tmem_base + lane_sel + h * kTileN;   // + (step & 1) * (kHalves * kTileN)
-    asm volatile("" : "+r"(par), "+r"(tfull_h), "+r"(cqfull_0), "+r"(cq_0), "+r"(taddr_h));
+    asm volatile("" : "+r"(par), "+r"(tfull_h), "+r"(cqfull_0), "+r"(taddr_h));
+    if constexpr (kPair) asm volatile("" : "+r"(cq_0));  // (the single-CTA form has no register to spare for it)
     // pair form: accumulator slots are released on the LEADER's barriers (the leader issues the MMAs)
     uint32_t tempty_rel0 = kPair ? mapa_shared(bar_tempty(0, h), 0) : bar_tempty(0, h);
     uint32_t tempty_rel1 = kPair ? mapa_shared(bar_tempty(1, h), 0) : bar_tempty(1, h);
@@ -406,8 +408,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int* const gthr = (kShare || kSeeded) ? a.row_thr + (qb * kBlockQ + h * kTileM + quad * 32 + lane) : nullptr;
       int published = kNoKey;
       int thr = thr_row ? min(kNoKey, __ldcg(gthr)) : kNoKey;
-      for (int t = t0; t < t1; ++t, ++step) {
-        if ((step & 1u) != par) continue;
+      // this warp takes every other tile of the unit: the ones whose global step has its parity
+      const uint32_t step_end = step + static_cast<uint32_t>(t1 - t0);
+      for (step += (par ^ step) & 1u; step < step_end; step += 2) {
         const uint32_t acc = step & 1u, bg = step % kBarGroups, bgph = (step / kBarGroups) & 1u;
         const uint32_t slot = step % kCqS, cqph = (step / kCqS) & 1u;
         mbar_wait(cqfull_0 + 8u * slot, cqph);  // landed long ago: returns at the first poll
@@ -441,6 +444,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
           thr = min(thr, g_next);
         }
       }
+      step = step_end;
       if (kSeeded && thr_row && best.d2 < kNoKey) atomicMin(gthr, best.d2);
       if (row < a.nq) {
         const int qn = a.qn[row];
