@@ -3,7 +3,7 @@
 # the database-sharded step.  Usage (under gpurun --gpus N): bash tools/run_multi.sh N [tag]
 set -u
 cd "$(dirname "$0")/.."
-N="${1:-8}"; TAG="${2:-r02}"
+N="${1:-8}"; TAG="${2:-r02}"; VARIANTS="${3:-yes}"
 OUT=gpurun_out; mkdir -p $OUT
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
 nvidia-smi --query-gpu=index,name,clocks.max.sm,power.limit --format=csv,noheader > $OUT/${TAG}_n${N}_smi.txt
@@ -11,6 +11,7 @@ nvidia-smi --query-gpu=index,name,clocks.max.sm,power.limit --format=csv,noheade
 (NCCL_DEBUG=WARN timeout 400 bash -c "$(declare -f run); N=$N run 29612 bench.py --gpus $N --steps 10 --warmup 3" > $OUT/${TAG}_bench_n${N}.json 2> $OUT/${TAG}_bench_n${N}.err; echo "exit $?" >> $OUT/${TAG}_bench_n${N}.err)
 i=0
 for variant in "--seed-rows 0" "--sweep-stages 1" "--exchange gather"; do
+  [ "$VARIANTS" = "yes" ] || break
   i=$((i+1))
   (timeout 300 bash -c "$(declare -f run); N=$N run $((29620+i)) bench.py --gpus $N --steps 10 --warmup 3 --no-alt --no-configs --no-parity-check $variant" > $OUT/${TAG}_bench_n${N}_v$i.json 2> $OUT/${TAG}_bench_n${N}_v$i.err; echo "exit $? ($variant)" >> $OUT/${TAG}_bench_n${N}_v$i.err)
 done
