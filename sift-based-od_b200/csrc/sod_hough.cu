@@ -202,19 +202,28 @@ __global__ void pose_bin_index_kernel(const double* __restrict__ pose, int64_t n
                 (static_cast<uint32_t>(it) << 16) | (static_cast<uint32_t>(is) << 24);
 }
 
-// Exclusive scan of n ints by one CTA, 32 consecutive elements per thread and round (n is the number
-// of Hough spaces or of compaction blocks: up to a few 100k, i.e. a handful of rounds of 32,768).
-constexpr int kScanItems = 32;
+// Exclusive scan of n ints.  One CTA scans rounds of 8,192 elements (8 consecutive per thread) and carries
+// the running total; `seed` (may be NULL) holds the value the first element starts from and `n_end` (may be
+// < 0) is where the grand total is written.  Small inputs (compaction blocks) take one launch of one CTA.
+// Large ones (the Hough spaces of a batch: up to a few 100k) take three: every CTA of a grid sums its own
+// 8,192-element tile (scan_tile_sums_kernel), one CTA scans the tile sums, and the same kernel runs again as
+// a grid with blockIdx.x selecting the tile and the scanned tile sum as its seed.
+constexpr int kScanItems = 8;
+constexpr int kScanTile = 1024 * kScanItems;
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ in,
                                                               int64_t n, int32_t* __restrict__ out,
                                                               int32_t* __restrict__ out_copy,
-                                                              int32_t* __restrict__ total) {
+                                                              int32_t* __restrict__ total,
+                                                              const int32_t* __restrict__ tile_seed) {
   __shared__ int32_t warp_sums[32];
   __shared__ int32_t carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
+  // grid form: this CTA owns tile blockIdx.x only and starts from the scanned sum of the tiles before it
+  const int64_t first = tile_seed ? static_cast<int64_t>(blockIdx.x) * kScanTile : 0;
+  const int64_t last = tile_seed ? (first + kScanTile < n ? first + kScanTile : n) : n;
+  if (threadIdx.x == 0) carry = tile_seed ? tile_seed[blockIdx.x] : 0;
   __syncthreads();
-  for (int64_t base = 0; base < n; base += static_cast<int64_t>(blockDim.x) * kScanItems) {
+  for (int64_t base = first; base < last; base += static_cast<int64_t>(blockDim.x) * kScanItems) {
     const int64_t i0 = base + static_cast<int64_t>(threadIdx.x) * kScanItems;
     int32_t v[kScanItems];
     int32_t sum = 0;
@@ -254,10 +263,45 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
     if (threadIdx.x == 0) carry += warp_sums[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && last == n) {
     out[n] = carry;
     if (total) *total = carry;
   }
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                              int32_t* __restrict__ tile_sums) {
+  __shared__ int32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanItems;
+  int32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) sum += i0 + k < n ? in[i0 + k] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) warp_sums[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t w = warp_sums[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) tile_sums[blockIdx.x] = w;
+  }
+}
+
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total); tile_ws: 2 * (ceil(n / kScanTile) + 1) ints.
+cudaError_t device_exclusive_scan(const int32_t* in, int64_t n, int32_t* out, int32_t* tile_ws, cudaStream_t st) {
+  const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+  if (tiles <= 2 || !tile_ws) {
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(in, n, out, nullptr, nullptr, nullptr);
+    return cudaGetLastError();
+  }
+  int32_t* sums = tile_ws;
+  int32_t* seeds = tile_ws + tiles + 1;
+  scan_tile_sums_kernel<<<static_cast<unsigned>(tiles), 1024, 0, st>>>(in, n, sums);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(sums, tiles, seeds, nullptr, nullptr, nullptr);
+  exclusive_scan_kernel<<<static_cast<unsigned>(tiles), 1024, 0, st>>>(in, n, out, nullptr, nullptr, seeds);
+  return cudaGetLastError();
 }
 
 // Counting-sort scatter: match id and its base bin travel together, so that the voting kernel reads
@@ -551,10 +595,12 @@ __global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const Fini
         s_m[j][t] = x;
       }
       first = s_m[0][t];
+      Member6 next = load_member(a, first);   // the rows of member j + 1 are in flight while j's chain runs
       for (int j = 0; j < cnt; ++j) {
         const int m = s_m[j][t];
         a.members[off + j] = m;
-        const Member6 v = load_member(a, m);
+        const Member6 v = next;
+        if (j + 1 < cnt) next = load_member(a, s_m[j + 1][t]);
         const double rcp = __drcp_rn(static_cast<double>(j + 1));
 #pragma unroll
         for (int c = 0; c < 6; ++c) mean[c] = j == 0 ? v.v[c] : running_mean(mean[c], v.v[c], j, rcp);
@@ -788,6 +834,7 @@ size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
   int32_t *group_of, *group_count, *group_off, *group_rank, *grouped, *members_raw, *ticket, *big_list, *huge_list;
+  int32_t* scan_tiles;
   uint32_t *grouped_base, *rank;
   uint16_t* creator;
   double* match_size;
@@ -808,6 +855,7 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.group_count = static_cast<int32_t*>(take((groups + 1) * 4));
   w.group_off = static_cast<int32_t*>(take((groups + 1) * 4));
   w.group_rank = static_cast<int32_t*>(take(m * 4));
+  w.scan_tiles = static_cast<int32_t*>(take(2 * ((groups + kScanTile - 1) / kScanTile + 2) * 4));
   w.grouped = static_cast<int32_t*>(take(m * 4));
   w.grouped_base = static_cast<uint32_t*>(take(m * 4));
   w.rank = static_cast<uint32_t*>(take(m * 16 * 4));
@@ -850,7 +898,7 @@ int sod_compact_matches(const int32_t* idx, const uint8_t* pass, int64_t n_query
   compact_count_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(idx, pass, n_query, t_lo,
                                                                                   t_hi, counts);
   SOD_CHECK_LAUNCH("compact_count_kernel");
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, blocks, offs, nullptr, n_out);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, blocks, offs, nullptr, n_out, nullptr);
   SOD_CHECK_LAUNCH("exclusive_scan_kernel");
   compact_write_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(
       idx, pass, n_query, t_lo, t_hi, offs, match_q, match_t);
@@ -962,8 +1010,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   stage_begin(SOD_STAGE_HOUGH_PREP, st);
   hough_pose_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(pa);
   SOD_CHECK_LAUNCH("hough_pose_kernel");
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.group_count, n_groups, w.group_off, nullptr, nullptr);
-  SOD_CHECK_LAUNCH("exclusive_scan_kernel");
+  SOD_CHECK_CUDA(device_exclusive_scan(w.group_count, n_groups, w.group_off, w.scan_tiles, st));
   group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
       w.group_of, w.group_rank, out->base_bin, n_matches_dev, n_matches, w.group_off, w.grouped, w.grouped_base);
   SOD_CHECK_LAUNCH("group_scatter_kernel");
