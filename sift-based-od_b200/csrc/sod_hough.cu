@@ -559,7 +559,7 @@ __device__ __forceinline__ double running_mean(double mean, double v, int j, dou
 // reference's append order) in a private strip of shared memory, run the six sequential running means
 // of PoseBin.update_posebin and compute the insertion-order key.  Single-vote bins (the majority) skip
 // the sort; larger bins are queued for the warp-per-bin and CTA-per-bin kernels.
-__global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const FinishArgs a) {
+__global__ void __launch_bounds__(kFinishThreads, 10) hough_finish_kernel(const FinishArgs a) {
   __shared__ int s_m[kSmallBin][kFinishThreads + 1];  // column = thread: conflict-free for equal rows
   int64_t n_bins = a.counters[0];
   if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
@@ -595,12 +595,10 @@ __global__ void __launch_bounds__(kFinishThreads) hough_finish_kernel(const Fini
         s_m[j][t] = x;
       }
       first = s_m[0][t];
-      Member6 next = load_member(a, first);   // the rows of member j + 1 are in flight while j's chain runs
       for (int j = 0; j < cnt; ++j) {
         const int m = s_m[j][t];
         a.members[off + j] = m;
-        const Member6 v = next;
-        if (j + 1 < cnt) next = load_member(a, s_m[j + 1][t]);
+        const Member6 v = load_member(a, m);
         const double rcp = __drcp_rn(static_cast<double>(j + 1));
 #pragma unroll
         for (int c = 0; c < 6; ++c) mean[c] = j == 0 ? v.v[c] : running_mean(mean[c], v.v[c], j, rcp);
@@ -1044,7 +1042,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   fa.list_count = w.ticket + 1;
   fa.big_cap = w.big_cap;
   stage_begin(SOD_STAGE_HOUGH_FINISH, st);
-  hough_finish_kernel<<<sms * 16, kFinishThreads, 0, st>>>(fa);
+  hough_finish_kernel<<<sms * 20, kFinishThreads, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_kernel");
   hough_finish_big_kernel<<<sms * 8, kBigWarps * 32, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_big_kernel");

@@ -97,3 +97,23 @@ def test_product_does_not_import_the_oracle():
 def test_graft_entry_build():
     import __graft_entry__ as g
     g.build()
+
+
+def test_option_and_exchange_argument_checks():
+    """Entry points added in round 2 reject bad arguments before touching the device (no GPU needed)."""
+    import ctypes as C
+    from sod_b200._capi import lib
+    assert lib.sod_set_option(b"no_such_option", 1) == -1 and b"unknown option" in lib.sod_last_error()
+    assert lib.sod_get_option(b"no_such_option") == -1
+    assert lib.sod_set_option(None, 1) == -1
+    assert lib.sod_exchange_bytes(1000, 0) == 0 and lib.sod_exchange_bytes(1000, 17) == 0
+    assert lib.sod_exchange_bytes(1000, 8) == 512 + 2 * 8 * 1000 * 16
+    table = (C.c_void_p * 2)(0, 0)
+    assert lib.sod_top2_exchange_peer(None, None, 10, 2, 2, C.cast(table, C.c_void_p), 100, None, None, None, None,
+                                      0.75, None) == -1                       # rank out of range
+    assert lib.sod_top2_exchange_peer(None, None, 101, 0, 2, C.cast(table, C.c_void_p), 100, None, None, None, None,
+                                      0.75, None) == -1 and b"capacity" in lib.sod_last_error()
+    assert lib.sod_top2_exchange_peer(None, None, 0, 0, 2, C.cast(table, C.c_void_p), 100, None, None, None, None,
+                                      0.75, None) == 0                        # empty batch: nothing to do
+    assert lib.sod_timing_read(99, None, 0) == -1
+    assert lib.sod_exchange_alloc(16, None) == -1
