@@ -348,7 +348,7 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
         nq = hi - lo
     pipe = DetectionPipeline(make_database(wl), nq, wl["frame_wh"], rank=rank, world=world, device=device,
                              shard=shard, exchange=args.exchange, result_rows="own", seed_rows=args.seed_rows,
-                             sweep_stages=args.sweep_stages)
+                             sweep_stages=args.sweep_stages, thresholds=args.thresholds)
     host = {k: torch.from_numpy(np.ascontiguousarray(q[k])).pin_memory()
             for k in ("q_xy", "q_angle", "q_octave", "q_frame")}
     host["q_des"] = q["q_des"].cpu().pin_memory()
@@ -378,7 +378,8 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
     # a seeded database-sharded step launches the matcher several times: the seeding sweep, then the shard
     # sweep in pipe.sweep_stages tile ranges; kernel_ms is the SUM of the shard-sweep launches of a step
     seeded = pipe.seed_matcher is not None and nq >= pipe.seed_min_queries
-    per_step = 1 + pipe.sweep_stages if seeded else 1
+    stages = 1 if pipe.peer_thr is not None else pipe.sweep_stages
+    per_step = 1 + stages if seeded else 1
     mm = stage["match"][: len(stage["match"]) // per_step * per_step]
     n_steps = max(len(mm) // per_step, 1)
     sweeps = [sum(mm[i * per_step + (1 if seeded else 0):(i + 1) * per_step]) for i in range(len(mm) // per_step)]
@@ -682,8 +683,8 @@ def run_ours(args):
         achieved = ops / (m["sweep_ms"] * 1e-3) / 1e12
         par = ("single" if world == 1 else
                f"db-shard{world}: database rows split at object boundaries, query batch replicated (1/{world} uploaded per "
-               f"rank + NVLink all-gather), NCCL {'scatter' if args.exchange in ('auto', 'peer') else args.exchange} exchange of the "
-               f"shard-local top-2, Hough+affine by object"
+               f"rank + NVLink all-gather), pruning thresholds shared over peer memory, NCCL "
+               f"{'scatter' if args.exchange in ('auto', 'peer') else args.exchange} exchange of the shard-local top-2, Hough+affine by object"
                if args.shard == "db" else f"frame-shard{world}, database replicated, no collective")
         line = {
             "metric": METRIC, "value": nq_total * args.steps / (m["ms_total"] * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -706,7 +707,9 @@ def run_ours(args):
                          "kernel_ms": m["sweep_ms"],
                          "kernel_ms_what": "mean CUDA-event duration of the match_top2_kernel launch alone (sod_timing_*), "
                                            "max over ranks",
-                         "seed_sweep_ms": m["seed_ms"], "sweep_stages": pipe.sweep_stages if m["seed_ms"] else 1,
+                         "seed_sweep_ms": m["seed_ms"],
+                         "thresholds": ("none" if not m["seed_ms"] else "peer memory, rotated block order" if pipe.peer_thr is not None
+                                        else f"NCCL MIN all-reduce, {pipe.sweep_stages} sweep stage(s)"),
                          "peak_source": ("max(2 x MEASURED_PEAKS.bf16_tflops_sustained = %.1f, cuBLASLt int8 8192^3 GEMM "
                                          "measured in this run = %.1f); MEASURED_PEAKS.json has no int8 entry%s"
                                          % (2.0 * bf16_sus, int8_tops or 0.0, "" if peaks else " (file absent: 1400 fallback)")),
@@ -804,6 +807,8 @@ def main():
                     help="--shard db: rows of the replicated threshold-seeding sample (0 = off; default: pipeline's)")
     ap.add_argument("--sweep-stages", type=int, default=None,
                     help="--shard db with seeding: tile ranges of the shard sweep with a threshold all-reduce between them")
+    ap.add_argument("--thresholds", default="auto", choices=["auto", "peer", "allreduce"],
+                    help="--shard db with seeding: thresholds over peer memory (rotated block order) or NCCL all-reduces")
     ap.add_argument("--no-alt", action="store_true", help="N > 1: skip the sub-record of the other partition")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5 sub-records")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle spot check")

@@ -117,6 +117,24 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
                          int64_t tile_end, int32_t* row_thr, int32_t* out_idx, uint32_t* out_d2,
                          void* workspace, size_t workspace_bytes, sod_stream_t stream);
 
+/* sod_match_top2_range for a database sharded over several GPUs of one node, with the thresholds travelling
+ * over peer memory instead of a collective: row_thr is this rank's threshold array (read when a query block's
+ * sweep starts), peer_thr_host a HOST array of n_peers DEVICE pointers to the arrays of all ranks (own one
+ * included; peers mapped with sod_ipc_open).  When a query block's sweep ends, the 2nd best of each of its rows
+ * is min-ed into every rank's array (reductions over NVLink).  block_rotation (in query blocks of 256 rows)
+ * rotates the order in which this rank visits the blocks - rank r of G passes r * n_blocks / G - so that the
+ * ranks reach a block at different times and each prunes with what the earlier visitors found in THEIR shards:
+ * no all-reduce, no stage boundary, and on average 7/16 of the database is known to a block's sweep.  Values are
+ * 2nd-best distances of real rows, so results stay exact whatever the timing; the caller resets the array
+ * (0x7F7F7F7F) before each batch and alternates between two arrays from batch to batch (a peer may run a
+ * little ahead, never a whole batch: the exchange of the merged lists separates batches).  Applies to
+ * single-segment sweeps (large batches); n_peers = 0 is sod_match_top2_range. */
+int sod_match_top2_peer(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
+                        const int32_t* cq, int64_t n_db, int32_t db_index_base, int64_t tile_begin,
+                        int64_t tile_end, int32_t* row_thr, int32_t* const* peer_thr_host, int32_t n_peers,
+                        int64_t block_rotation, int32_t* out_idx, uint32_t* out_d2, void* workspace,
+                        size_t workspace_bytes, sod_stream_t stream);
+
 /* K3.  Merge n_parts candidate lists (parts_idx/parts_d2 are [n_parts][n_query][2], e.g. the
  * all-gathered shard-local results) into the global top-2 by (d2, idx) lexicographic order and
  * apply Lowe's ratio test exactly as the reference evaluates it (main.py:81-82):

@@ -102,6 +102,13 @@ struct MatchArgs {
   int n_qunits;        // query blocks per unit row: n_qblocks, or ceil(n_qblocks / 2) CTA pairs
   int n_seg;
   int idx_base;
+  // Threshold publishing over peer memory (database sharded over several GPUs, kSeeded sweeps): when a unit
+  // ends, the 2nd best of each of its rows is min-ed into EVERY rank's threshold array (own one included);
+  // unit_rot rotates the order in which this rank visits the query blocks, so that the ranks reach a block at
+  // different times and a later visitor prunes with what the earlier ones found in their shards.
+  int n_peers;
+  int unit_rot;
+  int32_t* peer_thr[SOD_EXCHANGE_MAX_RANKS];
 };
 
 // 3-input max: top2_chunk builds a balanced tree (depth 4) over 32 registers with them; the
@@ -269,7 +276,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       uint32_t step = 0, ucount = 0;
       for (int u = unit0; u < total_units; u += unit_step, ++ucount) {
         const int seg = u / a.n_qunits;
-        const int qu = u - seg * a.n_qunits;
+        int qu = u - seg * a.n_qunits + a.unit_rot;   // unit_rot < n_qunits (0 unless n_seg == 1)
+        if (qu >= a.n_qunits) qu -= a.n_qunits;
         const int qb = kPair ? qu * 2 + static_cast<int>(cta_rank) : qu;
         const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
         const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
@@ -392,7 +400,8 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     uint32_t step = 0, ucount = 1;
     for (int u = unit0; u < total_units; u += unit_step, ++ucount) {
       const int seg = u / a.n_qunits;
-      const int qu = u - seg * a.n_qunits;
+      int qu = u - seg * a.n_qunits + a.unit_rot;
+      if (qu >= a.n_qunits) qu -= a.n_qunits;
       const int qb = kPair ? qu * 2 + static_cast<int>(cta_rank) : qu;
       const int t0 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg) * a.n_tiles / a.n_seg);
       const int t1 = a.tile_begin + static_cast<int>(static_cast<int64_t>(seg + 1) * a.n_tiles / a.n_seg);
@@ -445,7 +454,15 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
       step = step_end;
-      if (kSeeded && thr_row && best.d2 < kNoKey) atomicMin(gthr, best.d2);
+      if (kSeeded && thr_row && best.d2 < kNoKey) {
+        if (a.n_peers > 0) {
+          // reductions over NVLink into every rank's array (no return value: fire and forget)
+          const int64_t slot = gthr - a.row_thr;
+          for (int p = 0; p < a.n_peers; ++p) atomicMin(a.peer_thr[p] + slot, best.d2);
+        } else {
+          atomicMin(gthr, best.d2);
+        }
+      }
       if (row < a.nq) {
         const int qn = a.qn[row];
         const int64_t o = ((static_cast<int64_t>(seg) * kParity + par) * a.nq + row) * 2;
@@ -864,6 +881,18 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
                          const int32_t* cq, int64_t n_db, int32_t db_index_base, int64_t tile_begin,
                          int64_t tile_end, int32_t* row_thr, int32_t* out_idx, uint32_t* out_d2,
                          void* workspace, size_t workspace_bytes, sod_stream_t stream) {
+  return sod_match_top2_peer(q, qn, n_query, db_sorted, cq, n_db, db_index_base, tile_begin, tile_end, row_thr, nullptr, 0,
+                             0, out_idx, out_d2, workspace, workspace_bytes, stream);
+}
+
+int sod_match_top2_peer(const uint8_t* q, const int32_t* qn, int64_t n_query, const uint8_t* db_sorted,
+                        const int32_t* cq, int64_t n_db, int32_t db_index_base, int64_t tile_begin,
+                        int64_t tile_end, int32_t* row_thr, int32_t* const* peer_thr_host, int32_t n_peers,
+                        int64_t block_rotation, int32_t* out_idx, uint32_t* out_d2, void* workspace,
+                        size_t workspace_bytes, sod_stream_t stream) {
+  SOD_CHECK_ARG(n_peers >= 0 && n_peers <= SOD_EXCHANGE_MAX_RANKS && (n_peers == 0 || (peer_thr_host && row_thr)),
+                "bad peer threshold table");
+  SOD_CHECK_ARG(block_rotation >= 0, "negative block rotation");
   SOD_CHECK_ARG(n_query >= 0 && n_db >= 0, "negative size");
   SOD_CHECK_ARG(n_query < (int64_t(1) << 31) - kBlockQ && n_db < (int64_t(1) << 31) - kTileN,
                 "size out of range");
@@ -923,6 +952,12 @@ int sod_match_top2_range(const uint8_t* q, const int32_t* qn, int64_t n_query, c
   a.n_qunits = p.n_qunits;
   a.n_seg = p.n_seg;
   a.idx_base = db_index_base;
+  // peer publishing and the rotated visiting order belong to single-segment sweeps (the seeded instance)
+  const bool peer_mode = n_peers > 0 && row_thr && p.n_seg == 1;
+  a.n_peers = peer_mode ? n_peers : 0;
+  a.unit_rot = peer_mode ? static_cast<int>((block_rotation / (pair ? 2 : 1)) % p.n_qunits) : 0;
+  for (int i = 0; i < SOD_EXCHANGE_MAX_RANKS; ++i) a.peer_thr[i] = (peer_mode && i < n_peers) ? peer_thr_host[i] : nullptr;
+  for (int i = 0; i < a.n_peers; ++i) SOD_CHECK_ARG(a.peer_thr[i], "null threshold array of rank %d", i);
 
   // The attribute is per device (a process may drive several), so it is set at every launch: ~1 us.
   const bool seeded = row_thr && p.n_seg == 1, share = a.row_thr && !seeded;

@@ -105,6 +105,8 @@ _PROTOS = {
     "sod_match_top2": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _p, _p, _p, C.c_size_t, _p]),
     "sod_row_thr_ints": (_i64, [_i64]),
     "sod_match_top2_range": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, C.c_size_t, _p]),
+    "sod_match_top2_peer": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i32, _i64, _i64, _p, _p, _i32, _i64, _p, _p, _p,
+                                      C.c_size_t, _p]),
     "sod_top2_merge": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, _p, C.c_double, _p]),
     "sod_top2_keys": (C.c_int, [_p, _p, _i64, _i64, _p, _p]),
     "sod_top2_merge_keys": (C.c_int, [_p, _i32, _i64, _p, _p]),

@@ -114,11 +114,13 @@ class Matcher:
         return self._ws, self._qn
 
     def top2(self, q_u8: torch.Tensor, tiles: tuple[int, int] | None = None, row_thr: torch.Tensor | None = None,
-             prepared: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+             prepared: bool = False, peer_table=None, block_rotation: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
         """-> (idx int32 [nq,2] global rows or -1, d2 int32 [nq,2] squared distances, -1 if none).
         tiles=(begin, end): sweep only these stored 128-row tiles; row_thr: threshold array from
         new_thresholds(), read at the start and updated (sod_match_top2_range); prepared=True reuses the
-        query norms of the previous call with the same queries."""
+        query norms of the previous call with the same queries.  peer_table (a ctypes array of device
+        pointers, one per rank, to the arrays that correspond to row_thr on every rank) + block_rotation:
+        thresholds travel over peer memory (sod_match_top2_peer)."""
         q_u8 = _require_cuda(q_u8, torch.uint8, "query descriptors")
         nq = int(q_u8.shape[0])
         t0, t1 = (0, self.n_tiles) if tiles is None else (int(tiles[0]), int(tiles[1]))
@@ -131,9 +133,11 @@ class Matcher:
         if self.events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.sod_match_top2_range(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n, s.index_base, t0, t1,
-                                       _ptr(row_thr), _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(), _stream()),
-              "sod_match_top2_range")
+        n_peers = 0 if peer_table is None else len(peer_table)
+        check(lib.sod_match_top2_peer(_ptr(q_u8), _ptr(qn), nq, _ptr(s.des), _ptr(s.cq), s.n, s.index_base, t0, t1,
+                                      _ptr(row_thr), None if peer_table is None else C.cast(peer_table, C.c_void_p),
+                                      n_peers, int(block_rotation), _ptr(idx), _ptr(d2), _ptr(ws), ws.numel(),
+                                      _stream()), "sod_match_top2_peer")
         if self.events is not None:
             e1.record()
             self.events.append((e0, e1))

@@ -18,35 +18,104 @@ from ._capi import check, lib
 HANDLE_BYTES = 64
 
 
-class PeerExchange:
-    def __init__(self, max_query: int, rank: int, world: int, group=None, device="cuda"):
+class PeerBuffer:
+    """`nbytes` of zeroed device memory owned by the library (cudaMalloc), exported as a CUDA IPC handle and
+    mapped by every other rank of the node: .ptrs[r] is rank r's buffer as this process sees it."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, group=None, device="cuda"):
         import torch.distributed as dist
-        self.max_query, self.rank, self.world = int(max_query), int(rank), int(world)
+        self.nbytes, self.rank, self.world, self.group = int(nbytes), int(rank), int(world), group
         self.device = torch.device(device)
-        nbytes = int(lib.sod_exchange_bytes(self.max_query, self.world))
-        if nbytes == 0:
-            raise ValueError(f"peer exchange supports at most 16 ranks, got {world}")
         own = C.c_void_p()
         with torch.cuda.device(self.device):
-            check(lib.sod_exchange_alloc(nbytes, C.byref(own)), "sod_exchange_alloc")
+            check(lib.sod_exchange_alloc(self.nbytes, C.byref(own)), "sod_exchange_alloc")
             self._own = own
             handle = (C.c_uint8 * HANDLE_BYTES)()
             check(lib.sod_ipc_export(own, C.cast(handle, C.c_void_p)), "sod_ipc_export")
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(handle), group=group)
             self._mapped = []
-            ptrs = []
+            self.ptrs = []
             for r, h in enumerate(handles):
                 if r == self.rank:
-                    ptrs.append(own.value)
+                    self.ptrs.append(own.value)
                     continue
                 buf = (C.c_uint8 * HANDLE_BYTES).from_buffer_copy(h)
                 p = C.c_void_p()
                 check(lib.sod_ipc_open(C.cast(buf, C.c_void_p), C.byref(p)), "sod_ipc_open")
                 self._mapped.append(p)
-                ptrs.append(p.value)
-        self._table = (C.c_void_p * self.world)(*ptrs)
+                self.ptrs.append(p.value)
         dist.barrier(group=group)        # every rank has mapped every buffer before anybody stores into one
+
+    def table(self, byte_offset: int = 0):
+        """ctypes array of `world` device pointers, every rank's buffer + byte_offset."""
+        return (C.c_void_p * self.world)(*[p + int(byte_offset) for p in self.ptrs])
+
+    def own_tensor(self, dtype: torch.dtype, numel: int, byte_offset: int = 0) -> torch.Tensor:
+        """A torch view of this rank's own buffer (no copy; the buffer outlives the tensor's users)."""
+        item = torch.empty(0, dtype=dtype).element_size()
+        typestr = {torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1", torch.float32: "<f4"}[dtype]
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "version": 2,
+                                        "data": (self.ptrs[self.rank] + int(byte_offset), False)}
+        assert byte_offset + numel * item <= self.nbytes
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free the own one (after a barrier: nobody may still store into it)."""
+        if self._own is None:
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._mapped:
+            lib.sod_ipc_close(p)
+        lib.sod_exchange_free(self._own)
+        self._own, self._mapped = None, []
+
+
+class PeerThresholds:
+    """The pruning thresholds of a database-sharded run in peer memory (sod_match_top2_peer): two arrays per
+    rank, alternating from batch to batch; a sweep min-reduces what it finds into every rank's array."""
+
+    def __init__(self, max_query: int, rank: int, world: int, group=None, device="cuda"):
+        self.cap = max(int(lib.sod_row_thr_ints(max_query)), 1)
+        self.buf = PeerBuffer(2 * self.cap * 4, rank, world, group, device)
+        self.rank, self.world = rank, world
+        self._views = [self.buf.own_tensor(torch.int32, self.cap, k * self.cap * 4) for k in range(2)]
+        self._tables = {}
+        self.batch = 0
+
+    def begin_batch(self) -> torch.Tensor:
+        """Next batch: this rank's array of the batch's parity, reset to "none"."""
+        self.batch += 1
+        thr = self._views[self.batch & 1]
+        thr.fill_(0x7F7F7F7F)
+        return thr
+
+    def table(self, row_offset: int = 0):
+        """Pointers to every rank's array of the current batch, starting at query row `row_offset`."""
+        key = (self.batch & 1, int(row_offset))
+        t = self._tables.get(key)
+        if t is None:
+            t = self._tables[key] = self.buf.table(((self.batch & 1) * self.cap + int(row_offset)) * 4)
+        return t
+
+    def close(self) -> None:
+        self.buf.close()
+
+
+class PeerExchange:
+    def __init__(self, max_query: int, rank: int, world: int, group=None, device="cuda"):
+        self.max_query, self.rank, self.world = int(max_query), int(rank), int(world)
+        self.device = torch.device(device)
+        nbytes = int(lib.sod_exchange_bytes(self.max_query, self.world))
+        if nbytes == 0:
+            raise ValueError(f"peer exchange supports at most 16 ranks, got {world}")
+        self.buf = PeerBuffer(nbytes, rank, world, group, device)
+        self._table = self.buf.table()
         self.group = group
 
     def merge(self, idx: torch.Tensor, d2: torch.Tensor, ratio: float = E.RATIO):
@@ -66,14 +135,4 @@ class PeerExchange:
         return oi, od, dist_f, ok
 
     def close(self) -> None:
-        """Unmap the peers' buffers and free the own one (after a barrier: nobody may still store into it)."""
-        if self._own is None:
-            return
-        import torch.distributed as dist
-        torch.cuda.synchronize(self.device)
-        if dist.is_initialized():
-            dist.barrier(group=self.group)
-        for p in self._mapped:
-            lib.sod_ipc_close(p)
-        lib.sod_exchange_free(self._own)
-        self._own, self._mapped = None, []
+        self.buf.close()

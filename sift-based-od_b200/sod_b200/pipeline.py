@@ -95,7 +95,7 @@ class DetectionPipeline:
                  affine_threshold: int = 4, per_object_spaces: bool | None = None,
                  device: str | torch.device = "cuda", shard: str = "db", seed_rows: int | None = None,
                  exchange: str = "auto", replicated_host: bool = True, result_rows: str = "all",
-                 sweep_stages: int | None = None):
+                 sweep_stages: int | None = None, thresholds: str = "auto"):
         """Hough spaces.  The reference votes ALL model images into one dict (main.py:30,113-119: the
         database is several training views of one object), and that is the default here: one space
         per frame.  A multi-object database names the object of every model image in
@@ -111,7 +111,13 @@ class DetectionPipeline:
         seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
         seeds the pruning thresholds (see detect_device); 0 = off; None = SEED_ROWS_PER_RANK x world when the
         database has at least SEED_MIN_DB_ROWS rows.  Batches below SEED_MIN_QUERIES rows skip the seeding sweep.
-        sweep_stages (seeded runs only): the shard sweep runs in this many tile ranges with a MIN all-reduce
+        thresholds (seeded runs): how the ranks share pruning thresholds.  "peer" = over peer memory
+        (sod_match_top2_peer): a sweep min-reduces the 2nd best of every finished query block into every rank's
+        array with reductions over NVLink, and rank r visits the blocks in an order rotated by r/G, so that
+        each block is swept with what the earlier visitors found in their shards - no all-reduce, no stages;
+        "allreduce" = NCCL MIN all-reduces after the seeding sweep and between sweep_stages tile ranges;
+        "auto" = peer where the node can map peer memory, else allreduce.
+        sweep_stages (thresholds="allreduce" only): the shard sweep runs in this many tile ranges with a MIN all-reduce
         of the thresholds between them - after half of every shard the bound is the best 2nd best any rank
         has seen in half of the WHOLE database (B200, 8 x 125k rows: 14.5 ms in two stages against 15.7 ms
         in one, profiles/r02_seed_staged.txt); None = 2 for shards of up to 262,144 rows, else 1.
@@ -134,6 +140,8 @@ class DetectionPipeline:
             raise ValueError("exchange must be 'auto', 'peer', 'scatter' or 'gather'")
         if result_rows not in ("all", "own"):
             raise ValueError("result_rows must be 'all' or 'own'")
+        if thresholds not in ("auto", "peer", "allreduce"):
+            raise ValueError("thresholds must be 'auto', 'peer' or 'allreduce'")
         self.exchange = exchange
         self.replicated_host, self.result_rows = bool(replicated_host), result_rows
         self.seed_min_queries = SEED_MIN_QUERIES
@@ -235,6 +243,15 @@ class DetectionPipeline:
                 if self.exchange == "peer":
                     raise
                 self.peer_error = repr(exc)
+        self.peer_thr = None
+        if self.seed_matcher is not None and thresholds in ("auto", "peer"):
+            from .peer import PeerThresholds
+            try:
+                self.peer_thr = PeerThresholds(self.max_queries, rank, world, group, dev)
+            except Exception as exc:
+                if thresholds == "peer":
+                    raise
+                self.peer_error = repr(exc)
         self._graphs: dict = {}
         if world > 1 and (self.float_path or self.exchange == "gather"):
             self._gather_idx = torch.empty((world, self.max_queries, 2), dtype=torch.int32, device=dev)
@@ -244,7 +261,7 @@ class DetectionPipeline:
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
         self.launches_per_call = 18 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
-            (3 + (3 if self.sweep_stages > 1 else 0) if self.seed_matcher is not None else 0)
+            (3 + (3 if self.sweep_stages > 1 and self.peer_thr is None else 0) if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
     def _qset(self, slot: int) -> dict:
@@ -351,8 +368,20 @@ class DetectionPipeline:
             # upper bound of the final 2nd best and pruning with it is exact (ties pass); the sample's own
             # candidate lists are dropped - every sample row is found again by the rank that owns it.
             import torch.distributed as dist
-            thr = self.matcher.new_thresholds(n)
             s_lo, s_hi = seed_query_slice(n, self.rank, self.world)
+            if self.peer_thr is not None:
+                # Thresholds over peer memory.  The seeding sweep publishes the bounds of this rank's slice of the
+                # query rows into every rank's array; the shard sweep starts with the blocks of that same slice
+                # (rotation r/G) and publishes every finished block's 2nd best to everybody: a rank reaches the
+                # other slices after their seeds - and the other ranks' shard results for them - have arrived.
+                thr = self.peer_thr.begin_batch()
+                if s_hi > s_lo:
+                    self.seed_matcher.top2(q[s_lo:s_hi], None, thr[s_lo:], peer_table=self.peer_thr.table(s_lo))
+                blocks = (n + QUERY_BLOCK - 1) // QUERY_BLOCK
+                idx, d2 = self.matcher.top2(q, None, thr, peer_table=self.peer_thr.table(0),
+                                            block_rotation=blocks * self.rank // self.world)
+                return self._after_match(idx, d2, n, slot, _events, merge)
+            thr = self.matcher.new_thresholds(n)
             if s_hi > s_lo:
                 self.seed_matcher.top2(q[s_lo:s_hi], None, thr[s_lo:])
             dist.all_reduce(thr, op=dist.ReduceOp.MIN, group=self.group)
@@ -374,6 +403,10 @@ class DetectionPipeline:
                 idx, d2, _, _ = E.merge_top2(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
         else:
             idx, d2 = self.matcher.top2(q)
+        return self._after_match(idx, d2, n, slot, _events, merge)
+
+    def _after_match(self, idx, d2, n: int, slot: int, _events: bool, merge):
+        """Exchange of the shard-local lists, compaction, Hough, affine (the rest of detect_device)."""
         if self.world > 1 and self.peer is not None and n <= self.peer.max_query:
             # The exchange through peer memory: two kernels, no collective call (sod_b200/peer.py).
             idx, d2, dist_f, ok = self.peer.merge(idx, d2)

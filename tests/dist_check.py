@@ -57,16 +57,20 @@ def main():
                                     replicated_host=False).detect(*q), "whole-batch upload")
     # the same with threshold seeding forced on (it is automatic only for large databases and batches): a
     # replicated 1024-row sample, each rank seeds 1/G of the query rows, one min-reduce, then the shard sweep
-    seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024,
-                                    sweep_stages=2)
+    # thresholds over peer memory (the default where peer memory can be mapped): the seeding sweep and the shard
+    # sweep publish every finished block's 2nd best into every rank's array, block order rotated by rank
+    seeded_pipe = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024)
     seeded_pipe.seed_min_queries = 0
-    assert seeded_pipe.seed_matcher is not None
-    assert seeded_pipe.sweep_stages == 2                     # the shard sweep in two ranges + a mid all-reduce
+    assert seeded_pipe.seed_matcher is not None and seeded_pipe.peer_thr is not None, seeded_pipe.peer_error
     seeded = seeded_pipe.detect(*q)
-    one_stage = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024,
-                                  sweep_stages=1)
-    one_stage.seed_min_queries = 0
-    same(sharded, one_stage.detect(*q), "one-stage seeded sweep")
+    for _ in range(3):                                       # batch after batch: the two arrays alternate
+        same(sharded, seeded_pipe.detect(*q), "peer thresholds, repeated batch")
+    for stages in (2, 1):                                    # the NCCL form: all-reduce after seeding (+ mid-sweep)
+        ar = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024,
+                               sweep_stages=stages, thresholds="allreduce")
+        ar.seed_min_queries = 0
+        assert ar.peer_thr is None and ar.sweep_stages == stages
+        same(sharded, ar.detect(*q), f"all-reduce thresholds, {stages} stage(s)")
     # and with the gather form of the exchange (all-gather of the lists + merge on every rank)
     gathered_lists = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev,
                                        exchange="gather").detect(*q)

@@ -237,3 +237,41 @@ def test_peer_exchange_kernels_with_one_rank():
     finally:
         torch.cuda.synchronize()
         check(lib.sod_exchange_free(buf), "sod_exchange_free")
+
+
+def test_threshold_publishing_with_rotated_block_order():
+    """sod_match_top2_peer on ONE GPU playing two ranks in turn: rank 0 sweeps shard 0 and min-reduces every
+    finished block's 2nd best into both ranks' arrays, rank 1 then sweeps shard 1 with those bounds (and a
+    rotated block order).  The merged result equals the unsharded one; the bounds really travelled (rank 1's
+    array holds rank 0's values before rank 1 starts) and really pruned (rank 1 returns fewer candidates)."""
+    import ctypes as C
+    from sod_b200 import engine as E
+    from sod_b200._capi import lib
+    nq, ndb = 151_552, 20_000               # 296 block pairs = 4 full waves of 74 clusters: single-segment sweeps
+    g = torch.Generator(device="cuda").manual_seed(5)
+    def sift_gpu(n):
+        x = torch.randn((n, 128), device="cuda", generator=g).abs_()
+        x /= x.norm(dim=1, keepdim=True); x.clamp_(max=0.2); x /= x.norm(dim=1, keepdim=True)
+        return (x * 512).round_().clamp_(0, 255).to(torch.uint8)
+    db, q = sift_gpu(ndb), sift_gpu(nq)
+    q[:500] = db[torch.randint(0, ndb, (500,), device="cuda", generator=g)]
+    whole_i, whole_d = E.Matcher(E.prepare_db(db)).top2(q)
+    half = ndb // 2
+    m0 = E.Matcher(E.prepare_db(db[:half].contiguous(), index_base=0))
+    m1 = E.Matcher(E.prepare_db(db[half:].contiguous(), index_base=half))
+    thr0, thr1 = m0.new_thresholds(nq), m1.new_thresholds(nq)
+    table = (C.c_void_p * 2)(thr0.data_ptr(), thr1.data_ptr())
+    blocks = (nq + 255) // 256
+    i0, d0 = m0.top2(q, None, thr0, peer_table=table, block_rotation=0)
+    torch.cuda.synchronize()
+    assert torch.equal(thr0, thr1) and int((thr1[:nq] < 0x7F7F7F7F).sum()) == nq    # published to both arrays
+    qn = (q.int() ** 2).sum(1)
+    assert torch.equal(thr0[:nq], d0[:, 1] - qn)                                     # = the shard's 2nd best
+    i1, d1 = m1.top2(q, None, thr1, peer_table=table, block_rotation=blocks // 2)
+    plain_i1, _ = m1.top2(q)
+    assert int((i1 < 0).sum()) > int((plain_i1 < 0).sum())                           # the bounds pruned candidates
+    mi, md, _, _ = E.merge_top2(torch.stack([i0, i1]), torch.stack([d0, d1]))
+    assert torch.equal(mi, whole_i) and torch.equal(md, whole_d)
+    assert torch.equal(thr0, thr1)
+    full_second = whole_d[:, 1] - qn
+    assert bool((thr0[:nq] >= full_second).all())                                    # always upper bounds
