@@ -304,3 +304,53 @@ def test_shards_split_at_object_boundaries_when_objects_have_several_images():
     grp, n_local = local_hough_spaces(obj_of_img, 1, 3)
     assert n_local == 2 and grp.tolist() == [0, 0, 0, 0, 1, 1]
     np.testing.assert_array_equal(global_space_ids(np.array([0, 1, 2, 3]), 2, 3, 1), [1, 2, 4, 5])
+
+
+def test_rotated_block_order_with_published_thresholds_is_exact():
+    """Host logic of sod_match_top2_peer / DetectionPipeline's peer-threshold path, with numpy in the kernel's
+    place: G ranks each hold a shard, visit the query blocks in an order rotated by r/G, prune a block with the
+    thresholds published so far (the seed of the block's owner, then every earlier visitor's shard-local 2nd
+    best) and publish their own when the block is done.  Whatever the interleaving of the ranks, the merged
+    top-2 is the single-database result, and later visitors really see tighter bounds."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    sys.path.insert(0, str(ROOT / "sift-based-od_b200"))
+    from oracle import sod_oracle as O
+    from scenes import sift_like
+    from sod_b200.pipeline import seed_sample_rows
+    rng = np.random.default_rng(80)
+    world, block, n_blocks = 4, 16, 12
+    db = sift_like(rng, 900)
+    q = sift_like(rng, block * n_blocks)
+    db[17] = db[640] = q[3]                                   # a tie across shards
+    q[5:60] = np.clip(db[rng.integers(0, len(db), 55)].astype(np.int16) + rng.integers(-3, 4, (55, 128)), 0, 255).astype(np.uint8)
+    cuts = [0, 200, 450, 700, 900]
+    qn = (q.astype(np.int64) ** 2).sum(1)
+    none = np.int64(0x7F7F7F7F)
+    for order_seed in range(3):                               # three different interleavings of the ranks
+        thr = np.full(len(q), none)                           # what every rank's array converges to (min-reduce)
+        sample = db[seed_sample_rows(len(db), 32)]
+        _, sd = O.knn2(q, sample)                             # seeding: 2nd best on the replicated sample
+        thr = np.minimum(thr, sd[:, 1] - qn)
+        parts_i = np.full((world, len(q), 2), -1, np.int32)
+        parts_d = np.full((world, len(q), 2), -1, np.int64)
+        events = [(r, k) for r in range(world) for k in range(n_blocks)]
+        sched = np.random.default_rng(order_seed)
+        pos = [0] * world                                     # every rank walks ITS order; ranks interleave at random
+        tighter = 0
+        while any(p < n_blocks for p in pos):
+            r = int(sched.choice([x for x in range(world) if pos[x] < n_blocks]))
+            b = (n_blocks * r // world + pos[r]) % n_blocks   # rotation r / G
+            pos[r] += 1
+            rows = slice(b * block, (b + 1) * block)
+            lo, hi = cuts[r], cuts[r + 1]
+            tighter += int((thr[rows] < sd[rows, 1] - qn[rows]).sum())
+            idx, d2 = _pruned_top2(q[rows], db[lo:hi], lo, thr[rows])
+            parts_i[r, rows], parts_d[r, rows] = idx, d2
+            full_i, full_d = O.knn2(q[rows], db[lo:hi])       # what the rank publishes: its shard's own 2nd best
+            thr[rows] = np.minimum(thr[rows], np.where(full_i[:, 1] >= 0, full_d[:, 1] - qn[rows], none))
+        gi, gd = O.merge_top2(parts_i, parts_d)
+        ridx, rd2 = O.knn2(q, db)
+        np.testing.assert_array_equal(gi, ridx)
+        np.testing.assert_array_equal(gd, rd2)
+        assert tighter > 0 and int((parts_i < 0).sum()) > 0   # later visitors had tighter bounds, and they pruned
+    assert ridx[3].tolist() == [17, 640]
