@@ -559,7 +559,7 @@ __device__ __forceinline__ double running_mean(double mean, double v, int j, dou
 // reference's append order) in a private strip of shared memory, run the six sequential running means
 // of PoseBin.update_posebin and compute the insertion-order key.  Single-vote bins (the majority) skip
 // the sort; larger bins are queued for the warp-per-bin and CTA-per-bin kernels.
-__global__ void __launch_bounds__(kFinishThreads, 8) hough_finish_kernel(const FinishArgs a) {
+__global__ void __launch_bounds__(kFinishThreads, 10) hough_finish_kernel(const FinishArgs a) {
   __shared__ int s_m[kSmallBin][kFinishThreads + 1];  // column = thread: conflict-free for equal rows
   int64_t n_bins = a.counters[0];
   if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
@@ -585,26 +585,14 @@ __global__ void __launch_bounds__(kFinishThreads, 8) hough_finish_kernel(const F
 #pragma unroll
       for (int c = 0; c < 6; ++c) mean[c] = v.v[c];
     } else {
-      // all members are requested before the first one is looked at (a dependent load per member would cost a
-      // DRAM round trip each), then sorted by insertion in the shared-memory strip: a few elements, runtime
-      // bounds, no wasted slots
-      int raw[kSmallBin];
-#pragma unroll
-      for (int i = 0; i < kSmallBin; ++i) raw[i] = i < cnt ? a.members_raw[off + i] : 0;
-#pragma unroll
-      for (int i = 0; i < kSmallBin; ++i) {
-        if (i < cnt) {
-          // the rows the mean chains will read: in flight long before they are needed
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pose + static_cast<int64_t>(raw[i]) * 4));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.match_size + static_cast<int64_t>(raw[i]) * 2));
-          const int x = raw[i];
-          int j = i;
-          while (j > 0 && s_m[j - 1][t] > x) {
-            s_m[j][t] = s_m[j - 1][t];
-            --j;
-          }
-          s_m[j][t] = x;
+      for (int i = 0; i < cnt; ++i) {  // insertion sort: a few elements, runtime bounds, no wasted slots
+        const int x = a.members_raw[off + i];
+        int j = i;
+        while (j > 0 && s_m[j - 1][t] > x) {
+          s_m[j][t] = s_m[j - 1][t];
+          --j;
         }
+        s_m[j][t] = x;
       }
       first = s_m[0][t];
       for (int j = 0; j < cnt; ++j) {
