@@ -641,8 +641,8 @@ __device__ __forceinline__ void warp_means5(const FinishArgs& a, const int32_t* 
   }
 }
 
-// Bins of 17 .. kWarpBin votes: a warp takes five of them; each is rank-sorted by the whole warp out of a
-// shared-memory copy (ids are distinct), then the five mean chains run side by side.
+// Bins of 17 .. kWarpBin votes: a warp takes five of them; each is sorted by the whole warp in a
+// shared-memory copy (bitonic), then the five mean chains run side by side.
 constexpr int kBigWarps = 4;
 __global__ void __launch_bounds__(kBigWarps * 32) hough_finish_big_kernel(const FinishArgs a) {
   __shared__ int32_t s_raw[kBigWarps][kWarpBin];
@@ -664,15 +664,28 @@ __global__ void __launch_bounds__(kBigWarps * 32) hough_finish_big_kernel(const 
       cnt[i] = a.bin_count[rec[i]];
       const int32_t* raw = a.members_raw + off;
       int32_t* out = a.members + off;
-      for (int j = lane; j < cnt[i]; j += 32) s_raw[w][j] = raw[j];
+      SOD_DCHECK(cnt[i] <= kWarpBin);
+      // bitonic sort of the bin's ids in the warp's strip of shared memory, padded with INT_MAX to a power of
+      // two: n log^2 n / 64 compare-exchanges per lane instead of the n^2 / 32 compares of a rank sort
+      int padded = 32;
+      while (padded < cnt[i]) padded <<= 1;
+      int32_t* sm = s_raw[w];
+      for (int j = lane; j < padded; j += 32) sm[j] = j < cnt[i] ? raw[j] : INT_MAX;
       __syncwarp();
-      for (int j = lane; j < cnt[i]; j += 32) {
-        const int32_t x = s_raw[w][j];
-        int rank = 0;
-        for (int q = 0; q < cnt[i]; ++q) rank += s_raw[w][q] < x;
-        SOD_DCHECK(rank < cnt[i] && cnt[i] <= kWarpBin);
-        out[rank] = x;
+      for (int k = 2; k <= padded; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = lane; t < (padded >> 1); t += 32) {
+            const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+            const int32_t x = sm[lo], y = sm[hi];
+            if ((x > y) == ((lo & k) == 0)) {
+              sm[lo] = y;
+              sm[hi] = x;
+            }
+          }
+          __syncwarp();
+        }
       }
+      for (int j = lane; j < cnt[i]; j += 32) out[j] = sm[j];
       __syncwarp();
       sorted[i] = out;
     }
