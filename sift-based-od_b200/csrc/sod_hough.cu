@@ -628,12 +628,24 @@ __device__ __forceinline__ void warp_means5(const FinishArgs& a, const int32_t* 
   for (int i = 0; i < 5; ++i)
     if (k == i) { mine = sorted[i]; n = cnt[i]; my_rec = rec[i]; }
   if (k >= 5) n = 0;
+  // The values of the next eight members are requested while the current eight are folded in: a step of the
+  // chain is ~100 cycles of dependent arithmetic, a random row read from L2 / HBM several hundred.
+  constexpr int kAhead = 8;
   double mean = 0.0;
-  double next = n > 0 ? member_component(a, mine[0], c) : 0.0;
-  for (int j = 0; j < n; ++j) {
-    const double v = next;
-    if (j + 1 < n) next = member_component(a, mine[j + 1], c);
-    mean = j == 0 ? v : running_mean(mean, v, j, __drcp_rn(static_cast<double>(j + 1)));
+  double cur[kAhead];
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) cur[k] = k < n ? member_component(a, mine[k], c) : 0.0;
+  for (int base = 0; base < n; base += kAhead) {
+    double nxt[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) nxt[k] = base + kAhead + k < n ? member_component(a, mine[base + kAhead + k], c) : 0.0;
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+      const int j = base + k;
+      if (j < n) mean = j == 0 ? cur[k] : running_mean(mean, cur[k], j, __drcp_rn(static_cast<double>(j + 1)));
+    }
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) cur[k] = nxt[k];
   }
   if (n > 0) {
     a.bin_mean[my_rec * 6 + c] = mean;
