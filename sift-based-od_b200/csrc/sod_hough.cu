@@ -512,10 +512,6 @@ struct FinishArgs {
   int32_t* huge_list;    // larger bins: one CTA each (hough_finish_huge_kernel)
   int32_t* list_count;   // [0] big, [1] huge
   int64_t big_cap;
-  // bins of <= kSmallBin votes sorted by size, so that the threads of a warp finish bins of EQUAL size
-  int32_t* class_total;  // [kSmallBin + 1] bins per size (entry 0 unused); zeroed per call
-  int32_t* chunk_off;    // [chunks][kSmallBin] start of the chunk's bins inside their size class
-  int32_t* sorted_rec;   // [n small bins] record ids, size 1 first
 };
 
 constexpr int kSmallBin = 16;    // bins up to this size are finished by a single thread
@@ -559,83 +555,27 @@ __device__ __forceinline__ double running_mean(double mean, double v, int j, dou
   return __fma_rn(r, rcp, q);
 }
 
-// Bin records are first ordered by size (a counting sort in two passes over chunks of kClassChunk records):
-// bins of one warp then have the same number of members, and its lanes run the same number of dependent
-// loads and mean steps (unsorted, 12 of 32 lanes were active per instruction on the stress configuration).
-// Bins of more than kSmallBin votes are queued for the warp-per-bin and CTA-per-bin kernels here.
-constexpr int kClassChunk = 2048;
-constexpr int kClassThreads = 256;
-
-__global__ void __launch_bounds__(kClassThreads) finish_count_kernel(const FinishArgs a) {
-  __shared__ int s_hist[kSmallBin + 1];
-  int64_t n_bins = a.counters[0];
-  if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
-  const int tid = threadIdx.x;
-  for (int64_t chunk = blockIdx.x; chunk * kClassChunk < n_bins; chunk += gridDim.x) {
-    if (tid <= kSmallBin) s_hist[tid] = 0;
-    __syncthreads();
-    for (int i = tid; i < kClassChunk; i += kClassThreads) {
-      const int64_t rec = chunk * kClassChunk + i;
-      if (rec >= n_bins) break;
-      const int cnt = a.bin_count[rec];
-      if (cnt < a.detail_min_count) continue;
-      if (cnt > kSmallBin) {
-        const bool huge = cnt > kWarpBin;
-        const int slot = atomicAdd(a.list_count + (huge ? 1 : 0), 1);
-        if (slot < a.big_cap) (huge ? a.huge_list : a.big_list)[slot] = static_cast<int32_t>(rec);
-      } else {
-        atomicAdd(&s_hist[cnt], 1);
-      }
-    }
-    __syncthreads();
-    if (tid >= 1 && tid <= kSmallBin)
-      a.chunk_off[chunk * kSmallBin + tid - 1] = s_hist[tid] ? atomicAdd(&a.class_total[tid], s_hist[tid]) : 0;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(kClassThreads) finish_scatter_kernel(const FinishArgs a) {
-  __shared__ int s_base[kSmallBin + 1], s_cur[kSmallBin + 1];
-  int64_t n_bins = a.counters[0];
-  if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    int run = 0;
-    for (int c = 1; c <= kSmallBin; ++c) {
-      s_base[c] = run;
-      run += a.class_total[c];
-    }
-  }
-  __syncthreads();
-  for (int64_t chunk = blockIdx.x; chunk * kClassChunk < n_bins; chunk += gridDim.x) {
-    if (tid >= 1 && tid <= kSmallBin) s_cur[tid] = s_base[tid] + a.chunk_off[chunk * kSmallBin + tid - 1];
-    __syncthreads();
-    for (int i = tid; i < kClassChunk; i += kClassThreads) {
-      const int64_t rec = chunk * kClassChunk + i;
-      if (rec >= n_bins) break;
-      const int cnt = a.bin_count[rec];
-      if (cnt < a.detail_min_count || cnt > kSmallBin) continue;
-      a.sorted_rec[atomicAdd(&s_cur[cnt], 1)] = static_cast<int32_t>(rec);
-    }
-    __syncthreads();
-  }
-}
-
-// One THREAD per bin of <= kSmallBin votes (almost all bins), in order of size: sort the members by match id
-// (the reference's append order) in a private strip of shared memory, run the six sequential running means
-// of PoseBin.update_posebin and compute the insertion-order key.  Single-vote bins (the majority) need no sort.
+// One THREAD per bin (almost all bins hold a handful of votes): sort the members by match id (the
+// reference's append order) in a private strip of shared memory, run the six sequential running means
+// of PoseBin.update_posebin and compute the insertion-order key.  Single-vote bins (the majority) skip
+// the sort; larger bins are queued for the warp-per-bin and CTA-per-bin kernels.
 __global__ void __launch_bounds__(kFinishThreads, 10) hough_finish_kernel(const FinishArgs a) {
   __shared__ int s_m[kSmallBin][kFinishThreads + 1];  // column = thread: conflict-free for equal rows
-  int64_t n_small = 0;
-  for (int c = 1; c <= kSmallBin; ++c) n_small += a.class_total[c];
-  if (a.counters[0] > a.cap_bins || a.counters[3]) n_small = 0;
+  int64_t n_bins = a.counters[0];
+  if (n_bins > a.cap_bins || a.counters[3]) n_bins = 0;
   const int t = threadIdx.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + t; i < n_small;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t rec = a.sorted_rec[i];
+  for (int64_t rec = static_cast<int64_t>(blockIdx.x) * blockDim.x + t; rec < n_bins;
+       rec += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int cnt = a.bin_count[rec];
+    if (cnt < a.detail_min_count) continue;
+    if (cnt > kSmallBin) {
+      const bool huge = cnt > kWarpBin;
+      const int slot = atomicAdd(a.list_count + (huge ? 1 : 0), 1);
+      if (slot < a.big_cap) (huge ? a.huge_list : a.big_list)[slot] = static_cast<int32_t>(rec);
+      continue;
+    }
     const int off = a.bin_offset[rec];
-    SOD_DCHECK(off >= 0 && cnt >= 1 && cnt <= kSmallBin);
+    SOD_DCHECK(off >= 0 && cnt >= 1);
     double mean[6];
     int first;
     if (cnt == 1) {
@@ -645,9 +585,9 @@ __global__ void __launch_bounds__(kFinishThreads, 10) hough_finish_kernel(const 
 #pragma unroll
       for (int c = 0; c < 6; ++c) mean[c] = v.v[c];
     } else {
-      for (int k = 0; k < cnt; ++k) {  // insertion sort: a few elements, runtime bounds, no wasted slots
-        const int x = a.members_raw[off + k];
-        int j = k;
+      for (int i = 0; i < cnt; ++i) {  // insertion sort: a few elements, runtime bounds, no wasted slots
+        const int x = a.members_raw[off + i];
+        int j = i;
         while (j > 0 && s_m[j - 1][t] > x) {
           s_m[j][t] = s_m[j - 1][t];
           --j;
@@ -917,7 +857,7 @@ size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct HoughWs {
   int32_t *group_of, *group_count, *group_off, *group_rank, *grouped, *members_raw, *ticket, *big_list, *huge_list;
-  int32_t *scan_tiles, *chunk_off, *sorted_rec;
+  int32_t* scan_tiles;
   uint32_t *grouped_base, *rank;
   uint16_t* creator;
   double* match_size;
@@ -948,9 +888,6 @@ HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes)
   w.big_cap = cap_votes / (kSmallBin + 1) + 1;
   w.big_list = static_cast<int32_t*>(take(w.big_cap * 4));
   w.huge_list = static_cast<int32_t*>(take((cap_votes / (kWarpBin + 1) + 1) * 4));
-  // at most one bin per vote: the classification scratch is sized by the votes
-  w.chunk_off = static_cast<int32_t*>(take((cap_votes / kClassChunk + 2) * kSmallBin * 4));
-  w.sorted_rec = static_cast<int32_t*>(take((cap_votes + 1) * 4));
   w.bytes = o;
   return w;
 }
@@ -1083,8 +1020,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   if (sms <= 0) return SOD_ERR_CUDA;
 
   SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_groups + 1) * 4, st));
-  // [0] vote ticket, [1] big-bin count, [2] huge-bin count, [8 ..] bins per size class
-  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 256, st));
+  SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 12, st));  // [0] vote ticket, [1] big-bin count, [2] huge-bin count
   PoseArgs pa;
   pa.sc = *scene;
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = n_matches_dev; pa.n_cap = n_matches;
@@ -1130,13 +1066,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   fa.detail_min_count = detail_min_count; fa.big_list = w.big_list; fa.huge_list = w.huge_list;
   fa.list_count = w.ticket + 1;
   fa.big_cap = w.big_cap;
-  fa.class_total = w.ticket + 8;
-  fa.chunk_off = w.chunk_off; fa.sorted_rec = w.sorted_rec;
   stage_begin(SOD_STAGE_HOUGH_FINISH, st);
-  finish_count_kernel<<<sms * 8, kClassThreads, 0, st>>>(fa);
-  SOD_CHECK_LAUNCH("finish_count_kernel");
-  finish_scatter_kernel<<<sms * 8, kClassThreads, 0, st>>>(fa);
-  SOD_CHECK_LAUNCH("finish_scatter_kernel");
   hough_finish_kernel<<<sms * 20, kFinishThreads, 0, st>>>(fa);
   SOD_CHECK_LAUNCH("hough_finish_kernel");
   hough_finish_big_kernel<<<sms * 8, kBigWarps * 32, 0, st>>>(fa);
