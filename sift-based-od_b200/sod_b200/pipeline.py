@@ -260,7 +260,10 @@ class DetectionPipeline:
         # our kernels per detect_device call; the key exchange of a database-sharded run is
         # three kernels instead of the one merge, a seeding sweep adds the norms of its query slice, one
         # match launch and its list merge
-        self.launches_per_call = 18 + (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
+        # (18 = norms, match, list merge, ratio merge, 3 x compaction, pose, scan, scatter, vote, 3 x finish, 3 x affine,
+        # records; +2 when the Hough spaces of a batch need the tiled three-launch scan)
+        self.launches_per_call = 18 + (2 if self.scene.n_groups > 16384 else 0) + \
+            (2 if world > 1 and not self.float_path and exchange != "gather" else 0) + \
             (3 + (3 if self.sweep_stages > 1 and self.peer_thr is None else 0) if self.seed_matcher is not None else 0)
 
     # ---------------------------------------------------------------- device-resident inputs
