@@ -27,25 +27,46 @@ class PeerBuffer:
         self.nbytes, self.rank, self.world, self.group = int(nbytes), int(rank), int(world), group
         self.device = torch.device(device)
         own = C.c_void_p()
+        self._own, self._mapped, self.ptrs = None, [], []
+        error = None
         with torch.cuda.device(self.device):
-            check(lib.sod_exchange_alloc(self.nbytes, C.byref(own)), "sod_exchange_alloc")
-            self._own = own
+            # Every step that can fail on ONE rank only (allocation, export, mapping) is followed by a collective
+            # agreement, so that the ranks either all use peer memory or all raise - never a mix that would
+            # leave some of them waiting in a collective the others do not enter.
             handle = (C.c_uint8 * HANDLE_BYTES)()
-            check(lib.sod_ipc_export(own, C.cast(handle, C.c_void_p)), "sod_ipc_export")
+            try:
+                check(lib.sod_exchange_alloc(self.nbytes, C.byref(own)), "sod_exchange_alloc")
+                self._own = own
+                check(lib.sod_ipc_export(own, C.cast(handle, C.c_void_p)), "sod_ipc_export")
+            except Exception as exc:
+                error = exc
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            self._mapped = []
-            self.ptrs = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.ptrs.append(own.value)
-                    continue
-                buf = (C.c_uint8 * HANDLE_BYTES).from_buffer_copy(h)
-                p = C.c_void_p()
-                check(lib.sod_ipc_open(C.cast(buf, C.c_void_p), C.byref(p)), "sod_ipc_open")
-                self._mapped.append(p)
-                self.ptrs.append(p.value)
-        dist.barrier(group=group)        # every rank has mapped every buffer before anybody stores into one
+            dist.all_gather_object(handles, None if error else bytes(handle), group=group)
+            if error is None and all(h is not None for h in handles):
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            self.ptrs.append(own.value)
+                            continue
+                        buf = (C.c_uint8 * HANDLE_BYTES).from_buffer_copy(h)
+                        p = C.c_void_p()
+                        check(lib.sod_ipc_open(C.cast(buf, C.c_void_p), C.byref(p)), "sod_ipc_open")
+                        self._mapped.append(p)
+                        self.ptrs.append(p.value)
+                except Exception as exc:
+                    error = exc
+            elif error is None:
+                error = RuntimeError("a peer rank could not allocate or export its exchange buffer")
+            flags = [None] * self.world
+            dist.all_gather_object(flags, error is None, group=group)   # also the barrier: everybody has mapped
+            if not all(flags):
+                for p in self._mapped:
+                    lib.sod_ipc_close(p)
+                if self._own is not None:
+                    lib.sod_exchange_free(self._own)
+                self._own, self._mapped, self.ptrs = None, [], []
+                raise RuntimeError(f"peer memory unavailable on rank(s) {[r for r, f in enumerate(flags) if not f]}: "
+                                   f"{error!r}")
 
     def table(self, byte_offset: int = 0):
         """ctypes array of `world` device pointers, every rank's buffer + byte_offset."""
