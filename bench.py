@@ -377,11 +377,12 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
     _capi.timing_enable(False)
     # a seeded database-sharded step launches the matcher several times: the seeding sweep, then the shard
     # sweep in pipe.sweep_stages tile ranges; kernel_ms is the SUM of the shard-sweep launches of a step
-    seeded = pipe.seed_matcher is not None and nq >= pipe.seed_min_queries
-    stages = 1 if pipe.peer_thr is not None else pipe.sweep_stages
-    per_step = 1 + stages if seeded else 1
+    big = nq >= pipe.seed_min_queries
+    seeded = pipe.seed_matcher is not None and big            # a seeding sweep in front of the shard sweep
+    shared = big and (pipe.seed_matcher is not None or pipe.peer_thr is not None)
+    stages = pipe.sweep_stages if (shared and pipe.peer_thr is None) else 1
+    per_step = (1 if seeded else 0) + stages
     mm = stage["match"][: len(stage["match"]) // per_step * per_step]
-    n_steps = max(len(mm) // per_step, 1)
     sweeps = [sum(mm[i * per_step + (1 if seeded else 0):(i + 1) * per_step]) for i in range(len(mm) // per_step)]
     seeds = mm[0::per_step] if seeded else []
     loc = torch.tensor([e0.elapsed_time(e1), float(np.mean(sweeps)) if sweeps else 0.0,
@@ -708,8 +709,10 @@ def run_ours(args):
                          "kernel_ms_what": "mean CUDA-event duration of the match_top2_kernel launch alone (sod_timing_*), "
                                            "max over ranks",
                          "seed_sweep_ms": m["seed_ms"],
-                         "thresholds": ("none" if not m["seed_ms"] else "peer memory, rotated block order" if pipe.peer_thr is not None
-                                        else f"NCCL MIN all-reduce, {pipe.sweep_stages} sweep stage(s)"),
+                         "thresholds": ("peer memory, rotated block order" + ("" if pipe.seed_matcher is not None else ", no seeding sweep")
+                                        if pipe.peer_thr is not None and world > 1 else
+                                        f"NCCL MIN all-reduce, {pipe.sweep_stages} sweep stage(s)" if pipe.seed_matcher is not None
+                                        else "none"),
                          "peak_source": ("max(2 x MEASURED_PEAKS.bf16_tflops_sustained = %.1f, cuBLASLt int8 8192^3 GEMM "
                                          "measured in this run = %.1f); MEASURED_PEAKS.json has no int8 entry%s"
                                          % (2.0 * bf16_sus, int8_tops or 0.0, "" if peaks else " (file absent: 1400 fallback)")),

@@ -244,7 +244,9 @@ class DetectionPipeline:
                     raise
                 self.peer_error = repr(exc)
         self.peer_thr = None
-        if self.seed_matcher is not None and thresholds in ("auto", "peer"):
+        self.share_thresholds = (world > 1 and not self.float_path and
+                                 (self.seed_matcher is not None or len(image) >= SEED_MIN_DB_ROWS))
+        if self.share_thresholds and thresholds in ("auto", "peer"):
             from .peer import PeerThresholds
             try:
                 self.peer_thr = PeerThresholds(self.max_queries, rank, world, group, dev)
@@ -361,7 +363,7 @@ class DetectionPipeline:
                                                                     qs["frame"])
         q = self.q_des[:n]
         merge = E.merge_top2_float if self.float_path else E.merge_top2
-        if self.seed_matcher is not None and n >= self.seed_min_queries:
+        if (self.seed_matcher is not None or self.peer_thr is not None) and n >= self.seed_min_queries:
             # Threshold seeding.  A shard-local sweep has to establish every query row's pruning threshold
             # from scratch - about 2 ln(rows) slow-path updates per row and SHARD, i.e. G times the
             # threshold work of one GPU holding the whole database.  Instead every rank sweeps the small
@@ -378,13 +380,13 @@ class DetectionPipeline:
                 # (rotation r/G) and publishes every finished block's 2nd best to everybody: a rank reaches the
                 # other slices after their seeds - and the other ranks' shard results for them - have arrived.
                 thr = self.peer_thr.begin_batch()
-                if s_hi > s_lo:
+                if self.seed_matcher is not None and s_hi > s_lo:
                     self.seed_matcher.top2(q[s_lo:s_hi], None, thr[s_lo:], peer_table=self.peer_thr.table(s_lo))
                 blocks = (n + QUERY_BLOCK - 1) // QUERY_BLOCK
                 idx, d2 = self.matcher.top2(q, None, thr, peer_table=self.peer_thr.table(0),
                                             block_rotation=blocks * self.rank // self.world)
                 return self._after_match(idx, d2, n, slot, _events, merge)
-            thr = self.matcher.new_thresholds(n)
+            thr = self.matcher.new_thresholds(n)       # (reached with a seed sample only: the NCCL form)
             if s_hi > s_lo:
                 self.seed_matcher.top2(q[s_lo:s_hi], None, thr[s_lo:])
             dist.all_reduce(thr, op=dist.ReduceOp.MIN, group=self.group)
