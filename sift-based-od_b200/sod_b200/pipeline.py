@@ -109,8 +109,8 @@ class DetectionPipeline:
         gives each rank its own frames (no collective at all); the pipeline then behaves exactly like a
         single-GPU one.
         seed_rows (shard="db", several ranks): size of a replicated sample of the whole database that
-        seeds the pruning thresholds (see detect_device); 0 = off; None = SEED_ROWS_PER_RANK x world when the
-        database has at least SEED_MIN_DB_ROWS rows.  Batches below SEED_MIN_QUERIES rows skip the seeding sweep.
+        seeds the pruning thresholds (see detect_device); 0 = off; None = 0 with the thresholds in peer memory,
+        SEED_ROWS_PER_RANK x world with the NCCL form, when the database has at least SEED_MIN_DB_ROWS rows.  Batches below SEED_MIN_QUERIES rows skip the seeding sweep.
         thresholds (seeded runs): how the ranks share pruning thresholds.  "peer" = over peer memory
         (sod_match_top2_peer): a sweep min-reduces the 2nd best of every finished query block into every rank's
         array with reductions over NVLink, and rank r visits the blocks in an order rotated by r/G, so that
@@ -186,16 +186,6 @@ class DetectionPipeline:
         else:
             self.shard = E.prepare_db(des_dev, index_base=self.row_lo)
             self.matcher = E.Matcher(self.shard)
-            # Database-sharded runs keep a small even sample of the WHOLE database on every rank; it only
-            # seeds pruning thresholds (detect_device).  The choice depends on the whole database and on
-            # the argument alone, so it is the same on every rank.
-            if seed_rows is None:
-                seed_rows = SEED_ROWS_PER_RANK * world if len(image) >= SEED_MIN_DB_ROWS else 0
-            if world > 1 and seed_rows > 0:
-                rows = seed_sample_rows(len(image), seed_rows)
-                sample = db.des[torch.from_numpy(rows)] if isinstance(db.des, torch.Tensor) else \
-                    torch.from_numpy(np.ascontiguousarray(np.asarray(db.des)[rows]))
-                self.seed_matcher = E.Matcher(E.prepare_db(sample.to(self.device).contiguous(), index_base=0))
         # two stages pay on short shard sweeps (<= 256k rows: 8 ranks x 125k gain 1.1 ms of 15.7); on a 500k-row
         # shard the second launch costs what the tighter bound saves (measured at 2 ranks)
         self.sweep_stages = (2 if self.row_hi - self.row_lo <= 262144 else 1) if self._sweep_stages_arg is None \
@@ -245,7 +235,7 @@ class DetectionPipeline:
                 self.peer_error = repr(exc)
         self.peer_thr = None
         self.share_thresholds = (world > 1 and not self.float_path and
-                                 (self.seed_matcher is not None or len(image) >= SEED_MIN_DB_ROWS))
+                                 (bool(seed_rows) or len(image) >= SEED_MIN_DB_ROWS or thresholds == "peer"))
         if self.share_thresholds and thresholds in ("auto", "peer"):
             from .peer import PeerThresholds
             try:
@@ -254,6 +244,20 @@ class DetectionPipeline:
                 if thresholds == "peer":
                     raise
                 self.peer_error = repr(exc)
+        # Database-sharded runs may keep a small even sample of the WHOLE database on every rank; it only seeds
+        # pruning thresholds (detect_device).  With the thresholds in peer memory the default is NO sample: the
+        # rotation makes every rank the first visitor of 1/G of the query blocks, and sweeping those without a
+        # seed costs less than the seeding sweep (8 x 125k rows: 13.4 ms per step against 13.8).  The choice
+        # depends on the whole database and on the arguments alone, so it is the same on every rank.
+        if not self.float_path:
+            if seed_rows is None:
+                seed_rows = 0 if (self.peer_thr is not None or len(image) < SEED_MIN_DB_ROWS) else \
+                    SEED_ROWS_PER_RANK * world
+            if world > 1 and seed_rows > 0:
+                rows = seed_sample_rows(len(image), seed_rows)
+                sample = db.des[torch.from_numpy(rows)] if isinstance(db.des, torch.Tensor) else \
+                    torch.from_numpy(np.ascontiguousarray(np.asarray(db.des)[rows]))
+                self.seed_matcher = E.Matcher(E.prepare_db(sample.to(self.device).contiguous(), index_base=0))
         self._graphs: dict = {}
         if world > 1 and (self.float_path or self.exchange == "gather"):
             self._gather_idx = torch.empty((world, self.max_queries, 2), dtype=torch.int32, device=dev)

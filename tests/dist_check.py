@@ -65,6 +65,13 @@ def main():
     seeded = seeded_pipe.detect(*q)
     for _ in range(3):                                       # batch after batch: the two arrays alternate
         same(sharded, seeded_pipe.detect(*q), "peer thresholds, repeated batch")
+    # the default of a large database: peer thresholds WITHOUT a seeding sample (forced here: the test database is
+    # small), i.e. only the rotation and the publishing of finished blocks
+    bare = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, thresholds="peer", seed_rows=0)
+    bare.seed_min_queries = 0
+    assert bare.peer_thr is not None and bare.seed_matcher is None
+    for _ in range(2):
+        same(sharded, bare.detect(*q), "peer thresholds without seeding")
     for stages in (2, 1):                                    # the NCCL form: all-reduce after seeding (+ mid-sweep)
         ar = DetectionPipeline(db, nq, wl["frame_wh"], rank=rank, world=world, device=dev, seed_rows=1024,
                                sweep_stages=stages, thresholds="allreduce")
