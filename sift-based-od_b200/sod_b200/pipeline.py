@@ -335,7 +335,10 @@ class DetectionPipeline:
         Batches that would use an NCCL exchange or threshold seeding are not captured (they are not
         launch-bound): they fall through to detect_device."""
         uses_nccl = self.world > 1 and not (self.peer is not None and n <= self.peer.max_query)
-        if uses_nccl or n == 0:
+        # shared thresholds alternate between two arrays on the HOST side (PeerThresholds.begin_batch): a
+        # captured graph would freeze one of them
+        shares = (self.seed_matcher is not None or self.peer_thr is not None) and n >= self.seed_min_queries
+        if uses_nccl or shares or n == 0:
             return self.detect_device(n, slot)
         cur = torch.cuda.current_stream(self.device)
         if self._loaded[slot] is not None:
