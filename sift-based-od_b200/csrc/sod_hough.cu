@@ -457,6 +457,86 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
   __syncthreads();
 }
 
+// The same four phases for a space of at most kVoteThreads matches (every space of the bench workload: a
+// (frame, object) pair holds a handful): one match per thread, so its base bin, ranks, creator bits and match
+// id stay in REGISTERS from phase to phase - the general form's stores and re-loads of a.rank / a.creator /
+// a.base_bin are dependent global round trips, which is all that a ten-match space costs.
+__device__ __forceinline__ void vote_space_small(const VoteArgs& a, uint32_t* hist, int64_t g, int beg, int end,
+                                                 int* s_counts) {
+  const Bins4 bins = a.bins;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int p = beg + tid;
+  const bool have = p < end;
+  if (tid == 0) s_counts[0] = s_counts[1] = s_counts[4] = s_counts[5] = 0;
+  __syncthreads();
+  uint32_t base = 0, rk[8];
+  int m = 0, my_votes = 0;
+  unsigned created = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rk[i] = 0u;
+  if (have) {
+    base = a.base_bin[p];
+    m = a.grouped[p];
+    for_each_vote(base, bins, [&](int o, int code) {
+      SOD_DCHECK(code >= 0 && code < bins.total());
+      const uint32_t r = atomicAdd(&hist[code], 1u);  // r < kVoteThreads: 16 bits hold it
+      rk[o >> 1] |= r << ((o & 1) * 16);
+      created |= (r == 0u ? 1u : 0u) << o;
+      ++my_votes;
+    });
+  }
+  int my_bins = __popc(created);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    my_bins += __shfl_xor_sync(0xffffffffu, my_bins, o);
+    my_votes += __shfl_xor_sync(0xffffffffu, my_votes, o);
+  }
+  if (lane == 0 && my_votes) {
+    atomicAdd(&s_counts[0], my_bins);
+    atomicAdd(&s_counts[1], my_votes);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s_counts[2] = atomicAdd(&a.counters[0], s_counts[0]);
+    s_counts[3] = atomicAdd(&a.counters[1], s_counts[1]);
+    s_counts[6] = (static_cast<int64_t>(s_counts[2]) + s_counts[0] <= a.cap_bins) &&
+                  (static_cast<int64_t>(s_counts[3]) + s_counts[1] <= a.cap_votes);
+    if (!s_counts[6]) a.counters[3] = 1;
+  }
+  __syncthreads();
+  const bool ok = s_counts[6] != 0;
+  const int rec_base = s_counts[2], vote_base = s_counts[3];
+  if (ok && created) {
+    for_each_vote(base, bins, [&](int o, int code) {
+      if (!(created >> o & 1u)) return;
+      const int cnt = static_cast<int>(hist[code]);
+      const int rec = rec_base + atomicAdd(&s_counts[4], 1);
+      const int off = vote_base + atomicAdd(&s_counts[5], cnt);
+      SOD_DCHECK(rec < a.cap_bins && static_cast<int64_t>(off) + cnt <= a.cap_votes);
+      a.bin_group[rec] = static_cast<int32_t>(g);
+      a.bin_code[rec] = code;
+      a.bin_count[rec] = cnt;
+      a.bin_offset[rec] = off;
+      hist[code] = static_cast<uint32_t>(off);
+    });
+  }
+  __syncthreads();
+  if (ok && have) {
+    for_each_vote(base, bins, [&](int o, int code) {
+      const uint32_t r = (rk[o >> 1] >> ((o & 1) * 16)) & 0xFFFFu;
+      SOD_DCHECK(static_cast<int64_t>(hist[code]) + r < a.cap_votes);
+      a.members_raw[hist[code] + r] = m;
+    });
+  }
+  __syncthreads();
+  if (created) {
+    for_each_vote(base, bins, [&](int o, int code) {
+      if (created >> o & 1u) hist[code] = 0u;
+    });
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteArgs a) {
   extern __shared__ uint32_t hist[];  // bins^4 counters, all zero between groups
   __shared__ int s_counts[8];
@@ -484,7 +564,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
     for (int li = 0; li < n_list; ++li) {
       const int64_t g = gbase + s_list[li];
       const int beg = a.group_off[g], end = a.group_off[g + 1];
-      if (end - beg <= 65535)
+      if (end - beg <= kVoteThreads)
+        vote_space_small(a, hist, g, beg, end, s_counts);
+      else if (end - beg <= 65535)
         vote_space<false>(a, hist, g, beg, end, s_counts);
       else
         vote_space<true>(a, hist, g, beg, end, s_counts);
