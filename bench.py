@@ -402,21 +402,23 @@ def measure(args, wl, shard, rank, world, local, device, barrier, with_clocks=Tr
         for _ in range(k):
             yield tuple(host[key] for key in order)
 
-    for out in pipe.detect_batches(host_steps(max(2, args.warmup // 2))):
+    for out in pipe.detect_batches(host_steps(max(3, args.warmup))):   # both buffer sets, staging, NCCL paths warm
         pass
     barrier()
     t0 = time.perf_counter()
+    stamps = [t0]
     for out in pipe.detect_batches(host_steps(args.steps)):
-        pass
+        stamps.append(time.perf_counter())
     barrier()
     e2e = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    batch_ms = [round((b - a) * 1e3, 3) for a, b in zip(stamps, stamps[1:])]   # this rank's result-to-result intervals
     byt = torch.tensor([h2d_rank, DetectionPipeline.fetched_bytes(out)], device=device, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(byt, op=dist.ReduceOp.SUM)
     return dict(pipe=pipe, nq=nq, nq_total=nq_total, ms_total=ms_total, sweep_ms=sweep_ms, seed_ms=seed_ms,
                 vote_ms=vote_ms, hough_other_ms=hough_other_ms, affine_ms=affine_ms, e2e_s=float(e2e.item()),
-                h2d=int(byt[0]), d2h=int(byt[1]), res=res, clocks=clocks, host=host, order=order,
+                h2d=int(byt[0]), d2h=int(byt[1]), res=res, clocks=clocks, host=host, order=order, batch_ms=batch_ms,
                 launches=pipe.launches_per_call)
 
 
@@ -698,7 +700,8 @@ def run_ours(args):
                        "parallelism": par,
                        "l2": "inputs larger than L2 (128 MB database + 164 MB queries per step)"},
             "e2e": {"value": nq_total * args.steps / m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"],
-                    "d2h_bytes_per_step": m["d2h"], "bytes": "summed over all ranks"},
+                    "d2h_bytes_per_step": m["d2h"], "bytes": "summed over all ranks",
+                    "batch_ms_rank0": m["batch_ms"]},
             "gpu_launches": m["launches"] * args.steps,
             "clocks": m["clocks"],
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
