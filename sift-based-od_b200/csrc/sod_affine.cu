@@ -35,14 +35,26 @@ struct AffineArgs {
 __global__ void affine_select_kernel(const AffineArgs a) {
   int64_t n_bins = a.hough_counters[0];
   if (n_bins > a.cap_bins || a.hough_counters[3]) n_bins = 0;
-  for (int64_t rec = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; rec < n_bins;
-       rec += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (a.bin_count[rec] < a.vote_threshold) continue;
-    const int v = atomicAdd(&a.out.counters[0], 1);
-    if (v < a.out.cap_valid)
-      a.out.valid_bin[v] = static_cast<int32_t>(rec);
-    else
-      a.out.counters[1] = 1;
+  // one atomic per warp: the surviving bins of 32 consecutive records take consecutive slots (a stress scene
+  // selects 1.6 M bins: as single same-address atomics with return they were 0.17 ms)
+  const unsigned lane = threadIdx.x & 31u;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u); base < n_bins;
+       base += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t rec = base + lane;
+    const bool take = rec < n_bins && a.bin_count[rec] >= a.vote_threshold;
+    const unsigned takers = __ballot_sync(0xffffffffu, take);
+    if (!takers) continue;
+    const int leader = __ffs(takers) - 1;
+    int first = 0;
+    if (static_cast<int>(lane) == leader) first = atomicAdd(&a.out.counters[0], __popc(takers));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    if (take) {
+      const int v = first + __popc(takers & ((1u << lane) - 1u));
+      if (v < a.out.cap_valid)
+        a.out.valid_bin[v] = static_cast<int32_t>(rec);
+      else
+        a.out.counters[1] = 1;
+    }
   }
 }
 
@@ -200,7 +212,15 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void affine_verify_kernel(const AffineArgs a) {
+constexpr int kAffineWarps = 4;    // warps per CTA of affine_verify_kernel
+constexpr int kAffineStage = 512;  // pairs of a bin whose coordinates a warp keeps in shared memory
+
+__global__ void __launch_bounds__(kAffineWarps * 32) affine_verify_kernel(const AffineArgs a) {
+  // (x, y) of the model point and (u, v) of the query point of the bin's first kAffineStage pairs: every pass
+  // reads each pair twice, and fetching it is three dependent gathers (member -> match -> keypoint) - a
+  // 400-pair bin spent its time waiting for them, pass after pass.  Pairs beyond the stage are gathered.
+  __shared__ float4 s_xyuv[kAffineWarps][kAffineStage];
+  float4* const stage = s_xyuv[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -228,8 +248,23 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
     const double y_ref = a.factor_y > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor_y) : inf;
     uint8_t* keep = a.out.member_keep + off;
     const int32_t* mem = a.members + off;
-    for (int j = lane; j < cnt; j += 32) keep[j] = 1;
+    __syncwarp();  // the previous bin's readers of the stage are done
+#pragma unroll 4
+    for (int j = lane; j < cnt; j += 32) {
+      keep[j] = 1;
+      if (j < kAffineStage) {
+        const int m = mem[j];
+        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+        stage[j] = make_float4(pm.x, pm.y, pq.x, pq.y);
+      }
+    }
     __syncwarp();
+    auto pair_of = [&](int j) -> float4 {
+      if (j < kAffineStage) return stage[j];
+      const int m = mem[j];
+      const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+      return make_float4(pm.x, pm.y, pq.x, pq.y);
+    };
     int alive = cnt, passes = 0, live = 0, singular = 0, on_edge = 0;
     double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
     while (true) {
@@ -237,9 +272,8 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
       double sxu = 0, syu = 0, su = 0, sxv = 0, syv = 0, sv = 0;
       for (int j = lane; j < cnt; j += 32) {
         if (!keep[j]) continue;
-        const int m = mem[j];
-        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
-        const double x = pm.x, y = pm.y, u = pq.x, w = pq.y;
+        const float4 c = pair_of(j);
+        const double x = c.x, y = c.y, u = c.z, w = c.w;
         sxx += x * x; sxy += x * y; sx += x; syy += y * y; sy += y; sn += 1.0;
         sxu += x * u; syu += y * u; su += u; sxv += x * w; syv += y * w; sv += w;
       }
@@ -251,12 +285,11 @@ __global__ void affine_verify_kernel(const AffineArgs a) {
       int removed = 0;
       for (int j = lane; j < cnt; j += 32) {
         if (!keep[j]) continue;
-        const int m = mem[j];
-        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
-        const double x = pm.x, y = pm.y;
+        const float4 c = pair_of(j);
+        const double x = c.x, y = c.y;
         const double ua = __dadd_rn(__dadd_rn(__dmul_rn(pu[0], x), __dmul_rn(pu[1], y)), pu[2]);
         const double va = __dadd_rn(__dadd_rn(__dmul_rn(pv[0], x), __dmul_rn(pv[1], y)), pv[2]);
-        const double du = fabs(ua - static_cast<double>(pq.x)), dv = fabs(va - static_cast<double>(pq.y));
+        const double du = fabs(ua - static_cast<double>(c.z)), dv = fabs(va - static_cast<double>(c.w));
         on_edge += residual_on_edge(du, dv, x_ref, y_ref) ? 1 : 0;
         if (du > x_ref || dv > y_ref) {
           keep[j] = 0;
@@ -382,7 +415,7 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
   SOD_CHECK_LAUNCH("affine_select_kernel");
   affine_verify_small_kernel<<<sms * 8, 128, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_verify_small_kernel");
-  affine_verify_kernel<<<sms * 8, 128, 0, st>>>(a);
+  affine_verify_kernel<<<sms * 5, kAffineWarps * 32, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_verify_kernel");
   return SOD_OK;
 }

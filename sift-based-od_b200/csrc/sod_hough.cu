@@ -88,7 +88,8 @@ struct PoseArgs {
   int32_t* counters;
   int32_t* group_of;
   int32_t* group_count;
-  int32_t* group_rank;  // [M] arrival rank of the match inside its Hough space (the counting sort's position)
+  int32_t* group_rank;  // [M] arrival rank of the match inside its sub-list (the counting sort's position)
+  int group_shift;      // log2 of the sub-counters per Hough space (group_sub_shift)
   double* match_size;  // [M][2] (w, h) of the match's model image, or nullptr: read again by the finish kernels
 };
 
@@ -166,8 +167,23 @@ __global__ void hough_pose_kernel(const PoseArgs a) {
       if (edge == 2) atomicAdd(&a.counters[4], 1);
     }
     if (a.group_of) {
-      a.group_of[i] = grp;
-      a.group_rank[i] = atomicAdd(&a.group_count[grp], 1);
+      // Position inside the Hough space = the counting atomic's return value.  Consecutive matches often
+      // belong to one space (a stress scene holds thousands per object): the lanes of a warp that share a
+      // space take their positions with ONE atomic (2 M same-address atomics with return were most of this
+      // kernel's time at C5).  The order inside a space is free - the finish kernels sort members by match id.
+      // A scene with few spaces would send all those atomics to a handful of L2 lines (500 spaces = 16 lines
+      // took 2 M atomics at C5: 0.3 ms).  Each space therefore owns 2^group_shift sub-counters, picked by the
+      // warp's number: the space's matches form that many sub-lists, laid out one after the other by the scan.
+      const int sub = (grp << a.group_shift) +
+                      (static_cast<int>(i >> 5) & ((1 << a.group_shift) - 1));  // the same for the whole warp
+      a.group_of[i] = sub;
+      const unsigned lane = threadIdx.x & 31u;
+      const unsigned peers = __match_any_sync(__activemask(), grp);
+      const int leader = __ffs(peers) - 1;
+      int first = 0;
+      if (static_cast<int>(lane) == leader) first = atomicAdd(&a.group_count[sub], __popc(peers));
+      first = __shfl_sync(peers, first, leader);
+      a.group_rank[i] = first + __popc(peers & ((1u << lane) - 1u));
     }
   }
 }
@@ -322,7 +338,8 @@ __global__ void group_scatter_kernel(const int32_t* __restrict__ group_of, const
 }
 
 struct VoteArgs {
-  const int32_t* group_off;  // [n_groups+1]
+  const int32_t* group_off;  // [(n_groups << group_shift) + 1]: space g = [group_off[g << shift], group_off[(g + 1) << shift])
+  int group_shift;
   const int32_t* grouped;    // match ids grouped by Hough space
   const uint32_t* base_bin;  // base bins in the same (grouped) order
   uint32_t* rank;            // per grouped position 16 slots: arrival rank of each of its votes in its bin
@@ -557,13 +574,13 @@ __global__ void __launch_bounds__(kVoteThreads, 1) hough_vote_kernel(const VoteA
     const int64_t gbase = static_cast<int64_t>(s_chunk) * a.group_chunk;
     if (gbase >= a.n_groups) break;
     if (tid < a.group_chunk && gbase + tid < a.n_groups &&
-        a.group_off[gbase + tid + 1] > a.group_off[gbase + tid])
+        a.group_off[(gbase + tid + 1) << a.group_shift] > a.group_off[(gbase + tid) << a.group_shift])
       s_list[atomicAdd(&s_nlist, 1)] = tid;
     __syncthreads();
     const int n_list = s_nlist;
     for (int li = 0; li < n_list; ++li) {
       const int64_t g = gbase + s_list[li];
-      const int beg = a.group_off[g], end = a.group_off[g + 1];
+      const int beg = a.group_off[g << a.group_shift], end = a.group_off[(g + 1) << a.group_shift];
       if (end - beg <= kVoteThreads)
         vote_space_small(a, hist, g, beg, end, s_counts);
       else if (end - beg <= 65535)
@@ -947,8 +964,17 @@ struct HoughWs {
   size_t bytes;
 };
 
+// Sub-counters per Hough space of the counting sort (hough_pose_kernel): up to 16, as long as all of them
+// fit 65,536 counters - scenes with many spaces spread their atomics by themselves.
+int group_sub_shift(int64_t groups) {
+  int shift = 0;
+  while (shift < 4 && (groups << (shift + 1)) <= 65536) ++shift;
+  return shift;
+}
+
 HoughWs carve_hough_ws(void* base, int64_t m, int64_t groups, int64_t cap_votes) {
   HoughWs w;
+  groups <<= group_sub_shift(groups);  // group_count / group_off / the scan hold one entry per sub-counter
   size_t o = 0;
   auto take = [&](size_t bytes) {
     void* p = base ? static_cast<char*>(base) + o : nullptr;
@@ -1027,7 +1053,7 @@ int sod_estimate_pose(const sod_scene* scene, const int32_t* match_q, const int3
   pa.match_q = match_q; pa.match_t = match_t; pa.n_dev = nullptr; pa.n_cap = n_matches;
   pa.bins = Bins4{bins, bins, bins, bins}; pa.sigma_lut = sigma_lut; pa.pose = pose; pa.base_bin = base_bin;
   pa.near_edge = near_edge; pa.counters = nullptr; pa.group_of = nullptr; pa.group_count = nullptr;
-  pa.group_rank = nullptr; pa.match_size = nullptr;
+  pa.group_rank = nullptr; pa.match_size = nullptr; pa.group_shift = 0;
   const int threads = 256;
   hough_pose_kernel<<<static_cast<unsigned>((n_matches + threads - 1) / threads), threads, 0,
                       static_cast<cudaStream_t>(stream)>>>(pa);
@@ -1101,7 +1127,9 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   const int sms = device_sm_count();
   if (sms <= 0) return SOD_ERR_CUDA;
 
-  SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_groups + 1) * 4, st));
+  const int group_shift = group_sub_shift(n_groups);
+  const int64_t n_sub = n_groups << group_shift;
+  SOD_CHECK_CUDA(cudaMemsetAsync(w.group_count, 0, (n_sub + 1) * 4, st));
   SOD_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, 12, st));  // [0] vote ticket, [1] big-bin count, [2] huge-bin count
   PoseArgs pa;
   pa.sc = *scene;
@@ -1109,13 +1137,14 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
   pa.bins = bins; pa.sigma_lut = sigma_lut; pa.pose = out->pose; pa.base_bin = out->base_bin;
   pa.near_edge = out->near_edge; pa.counters = out->counters; pa.group_of = w.group_of;
   pa.group_count = w.group_count; pa.group_rank = w.group_rank; pa.match_size = w.match_size;
+  pa.group_shift = group_shift;
   const int threads = 256;
   int64_t blocks = (n_matches + threads - 1) / threads;
   if (blocks > static_cast<int64_t>(sms) * 16) blocks = static_cast<int64_t>(sms) * 16;
   stage_begin(SOD_STAGE_HOUGH_PREP, st);
   hough_pose_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(pa);
   SOD_CHECK_LAUNCH("hough_pose_kernel");
-  SOD_CHECK_CUDA(device_exclusive_scan(w.group_count, n_groups, w.group_off, w.scan_tiles, st));
+  SOD_CHECK_CUDA(device_exclusive_scan(w.group_count, n_sub, w.group_off, w.scan_tiles, st));
   group_scatter_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
       w.group_of, w.group_rank, out->base_bin, n_matches_dev, n_matches, w.group_off, w.grouped, w.grouped_base);
   SOD_CHECK_LAUNCH("group_scatter_kernel");
@@ -1123,7 +1152,7 @@ int sod_hough_vote_dims(const sod_scene* scene, const int32_t* match_q, const in
 
   VoteArgs va;
   va.group_off = w.group_off; va.grouped = w.grouped; va.base_bin = w.grouped_base; va.rank = w.rank; va.creator = w.creator;
-  va.n_groups = n_groups; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
+  va.n_groups = n_groups; va.group_shift = group_shift; va.bins = bins; va.ticket = w.ticket; va.counters = out->counters; va.bin_group = out->bin_group;
   va.bin_code = out->bin_code; va.bin_count = out->bin_count; va.bin_offset = out->bin_offset;
   va.members_raw = w.members_raw; va.cap_bins = out->cap_bins; va.cap_votes = raw_cap;
   const size_t hist_bytes = static_cast<size_t>(bins.total()) * sizeof(uint32_t);
