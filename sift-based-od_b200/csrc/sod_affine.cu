@@ -133,7 +133,13 @@ __device__ __forceinline__ bool residual_on_edge(double du, double dv, double x_
 
 // One THREAD per small valid bin (the vast majority: random bins with 5-10 votes): the alive set is
 // a 32-bit mask, every pass re-gathers the coordinates of the alive pairs.
-__global__ void affine_verify_small_kernel(const AffineArgs a) {
+constexpr int kSmallThreads = 128;
+constexpr int kSmallStage = 16;  // pairs of a bin whose coordinates the thread keeps in shared memory
+
+__global__ void __launch_bounds__(kSmallThreads) affine_verify_small_kernel(const AffineArgs a) {
+  // coordinates of the bin's first kSmallStage pairs, fetched once (member -> match -> keypoint, three
+  // dependent gathers each) instead of twice per pass; [pair][thread] keeps the threads' rows in different banks
+  __shared__ float4 s_pairs[kSmallStage][kSmallThreads];
   int64_t n_valid = a.out.counters[0];
   if (n_valid > a.out.cap_valid) n_valid = a.out.cap_valid;
   const float2* mxy = reinterpret_cast<const float2*>(a.sc.model.xy);
@@ -157,6 +163,17 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
     const double x_ref = a.factor_x > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame] * isigma), a.factor_x) : inf;
     const double y_ref = a.factor_y > 0 ? __ddiv_rn(static_cast<double>(a.sc.frame_wh[2 * frame + 1] * isigma), a.factor_y) : inf;
     const int32_t* mem = a.members + off;
+    auto gather = [&](int j) -> float4 {
+      const int m = mem[j];
+      SOD_DCHECK(m >= 0 && a.match_t[m] >= 0 && a.match_t[m] < a.sc.model.n && a.match_q[m] >= 0 &&
+                 a.match_q[m] < a.sc.query.n);
+      const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
+      return make_float4(pm.x, pm.y, pq.x, pq.y);
+    };
+    const int n_stage = cnt < kSmallStage ? cnt : kSmallStage;
+#pragma unroll 4
+    for (int j = 0; j < n_stage; ++j) s_pairs[j][threadIdx.x] = gather(j);
+    auto pair_of = [&](int j) -> float4 { return j < kSmallStage ? s_pairs[j][threadIdx.x] : gather(j); };
     unsigned alive = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
     int n_alive = cnt, passes = 0, live = 0, singular = 0, on_edge = 0;
     double pu[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
@@ -165,11 +182,8 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
       double ru[3] = {0, 0, 0}, rv[3] = {0, 0, 0};
       for (int j = 0; j < cnt; ++j) {
         if (!(alive >> j & 1u)) continue;
-        const int m = mem[j];
-        SOD_DCHECK(m >= 0 && a.match_t[m] >= 0 && a.match_t[m] < a.sc.model.n && a.match_q[m] >= 0 &&
-                   a.match_q[m] < a.sc.query.n);
-        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
-        const double x = pm.x, y = pm.y, u = pq.x, w = pq.y;
+        const float4 c = pair_of(j);
+        const double x = c.x, y = c.y, u = c.z, w = c.w;
         sxx += x * x; sxy += x * y; sx += x; syy += y * y; sy += y; sn += 1.0;
         ru[0] += x * u; ru[1] += y * u; ru[2] += u; rv[0] += x * w; rv[1] += y * w; rv[2] += w;
       }
@@ -177,12 +191,11 @@ __global__ void affine_verify_small_kernel(const AffineArgs a) {
       int removed = 0;
       for (int j = 0; j < cnt; ++j) {
         if (!(alive >> j & 1u)) continue;
-        const int m = mem[j];
-        const float2 pm = mxy[a.match_t[m]], pq = qxy[a.match_q[m]];
-        const double x = pm.x, y = pm.y;
+        const float4 c = pair_of(j);
+        const double x = c.x, y = c.y;
         const double ua = __dadd_rn(__dadd_rn(__dmul_rn(pu[0], x), __dmul_rn(pu[1], y)), pu[2]);
         const double va = __dadd_rn(__dadd_rn(__dmul_rn(pv[0], x), __dmul_rn(pv[1], y)), pv[2]);
-        const double du = fabs(ua - static_cast<double>(pq.x)), dv = fabs(va - static_cast<double>(pq.y));
+        const double du = fabs(ua - static_cast<double>(c.z)), dv = fabs(va - static_cast<double>(c.w));
         on_edge += residual_on_edge(du, dv, x_ref, y_ref) ? 1 : 0;
         if (du > x_ref || dv > y_ref) {
           alive &= ~(1u << j);
@@ -228,12 +241,17 @@ __global__ void __launch_bounds__(kAffineWarps * 32) affine_verify_kernel(const 
   if (n_valid > a.out.cap_valid) n_valid = a.out.cap_valid;
   const float2* mxy = reinterpret_cast<const float2*>(a.sc.model.xy);
   const float2* qxy = reinterpret_cast<const float2*>(a.sc.query.xy);
-  // Almost every selected bin is a small one (affine_verify_small_kernel's): the lanes look at 32 list entries
-  // at a time and the warp then takes the big bins among them in turn.  (One entry per warp and step meant
+  // Almost every selected bin is a small one (affine_verify_small_kernel's): the lanes look at a window of up
+  // to 32 list entries at a time and the warp then takes the big bins among them in turn.  (One entry per warp and step meant
   // 1.6 M dependent look-ups spread over 3,000 warps at C5: 0.66 ms for 9,000 big bins.)
-  for (int64_t v0 = warp * 32; v0 < n_valid; v0 += n_warps * 32) {
+  // The window shrinks with the list (down to one entry per warp): a warp works through the big bins of its
+  // window one after the other, and a short list of mostly big bins (the bench workload: 16,500 entries) must
+  // still spread over all warps.
+  int width = 32;
+  while (width > 1 && n_valid < static_cast<int64_t>(width) * n_warps) width >>= 1;
+  for (int64_t v0 = warp * width; v0 < n_valid; v0 += n_warps * width) {
    int rec_l = 0, cnt_l = 0;
-   if (v0 + lane < n_valid) {
+   if (lane < width && v0 + lane < n_valid) {
      rec_l = a.out.valid_bin[v0 + lane];
      cnt_l = a.bin_count[rec_l];
    }
@@ -427,7 +445,7 @@ extern "C" int sod_affine_verify(const sod_scene* scene, const int32_t* match_q,
   StageScope timed(SOD_STAGE_AFFINE, st);
   affine_select_kernel<<<sms * 4, 256, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_select_kernel");
-  affine_verify_small_kernel<<<sms * 8, 128, 0, st>>>(a);
+  affine_verify_small_kernel<<<sms * 5, kSmallThreads, 0, st>>>(a);  // 5 CTAs per SM are resident (registers)
   SOD_CHECK_LAUNCH("affine_verify_small_kernel");
   affine_verify_kernel<<<sms * 5, kAffineWarps * 32, 0, st>>>(a);
   SOD_CHECK_LAUNCH("affine_verify_kernel");
