@@ -10,20 +10,21 @@ against 1,000 model objects x 1,000 descriptors, u8 128-d, synthetic (seeded).  
 4 planted object instances (10 % of its descriptors are true matches) plus 1 % descriptor-only false
 matches; Hough spaces are per (frame, object).  A step is one pass of the whole path over the batch.
 N > 1, two ways to partition the same fixed total work ("scaling": "strong"):
-  --shard frames (default)  the 128 MB database is replicated, every rank takes 1/N of the frames; the
-                            units are independent, so there is no data-path collective at all
-                            (r01: 91.6 % efficiency at 8 GPUs);
-  --shard db                database rows sharded object-aligned across ranks, queries replicated, one
-                            NCCL all-gather of the shard-local top-2 (16 B/query) + merge, Hough +
-                            affine for each rank's own objects (the layout a database that does not
-                            fit one GPU, or a single-frame latency query, needs; r01: 79 % at 8 GPUs,
-                            the loss is the per-shard restart of the pruning threshold).
+  --shard db (default)      the north star's layout: database rows sharded object-aligned across the ranks,
+                            the query batch replicated (each rank uploads 1/N of it, one all-gather over
+                            NVLink), shard-local top-2 merged by ONE exchange (16 B per query row), pruning
+                            thresholds shared over peer memory, Hough + affine for each rank's own objects;
+  --shard frames            the 128 MB database is replicated and every rank takes 1/N of the frames: no
+                            data-path collective at all.  The default run reports it as `alt_partition`.
+The scaling figures are stated once, in DESIGN.md §5 (builder runs under profiles/r02_bench_n*.json); the
+driver's SCALE_rNN.json is the authority.
 
 Timed regions
   value : inputs resident in HBM; CUDA events on the launching stream, barrier + synchronize on both
           sides, max over ranks.
-  e2e   : the public API (sod_b200.pipeline.DetectionPipeline.detect) with pinned HOST buffers:
-          H2D of descriptors + keypoints and D2H of matches + verified bins inside the region.
+  e2e   : the public API (sod_b200.pipeline.DetectionPipeline.detect_batches) with pinned HOST buffers:
+          H2D of descriptors + keypoints and D2H of matches + verified bins inside the region, every step;
+          pipelined one step deep (the copies of step i+1 overlap the kernels of step i).
 """
 from __future__ import annotations
 

@@ -477,7 +477,7 @@ __device__ __forceinline__ void vote_space(const VoteArgs& a, uint32_t* hist, in
 // The same four phases for a space of at most kVoteThreads matches (every space of the bench workload: a
 // (frame, object) pair holds a handful): one match per thread, so its base bin, ranks, creator bits and match
 // id stay in REGISTERS from phase to phase - the general form's stores and re-loads of a.rank / a.creator /
-// a.base_bin are dependent global round trips, which is all that a ten-match space costs.
+// a.base_bin are dependent global round trips, which is most of what a small space costs.
 __device__ __forceinline__ void vote_space_small(const VoteArgs& a, uint32_t* hist, int64_t g, int beg, int end,
                                                  int* s_counts) {
   const Bins4 bins = a.bins;
